@@ -1,0 +1,260 @@
+#!/usr/bin/env python
+"""bench.py -- cloud-march throughput (Mpix/s, ms/frame) of the B200 path, with its roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--filter exact|hw|hybrid]
+    python bench.py --impl reference ...      # the CPU arm: the oracle port on all host cores
+
+A "step" is one full-resolution frame (one MM_FULL dispatch of the cloud pass: every pixel marched).
+Default workload: BASELINE.json configs[1] = C2, 1920x1080, midday sun, shipped CloudPlacement (mean
+coverage 0.52), shipped noise volumes; see tests/scenes.py.  Inputs (4 textures, ~10 MB as bytes, 43 MB
+resident incl. the float copies) are far smaller than L2 by design of the workload, so the L2 is flushed
+between timed frames by writing a 256 MB buffer (config.l2: "flushed"); each frame is timed with its own
+CUDA event pair on the launching stream and the flush is outside the pairs.
+
+N > 1 (torchrun, one process per GPU): STRONG scaling -- the same frame is sharded row-cyclically
+(row block 2) over the ranks; every rank's kernel stores its pixels straight into rank 0's image over
+NVLink (CUDA-IPC mapped peer memory), so there is no separate gather collective.  Time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+TEXPEAK_QUADS_PER_CLK_PER_SM = 4
+N_SM = 148
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--filter", default="exact", choices=["exact", "hw", "hybrid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--row-block", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(s[2 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def workload_Q(oracle_binding, sc, rows_step):
+    """Algorithmic work per pixel: Q = N2D + 2*N3D bilinear-quad ops, from the oracle's counters on
+    a row subsample of the same frame (every rows_step-th row)."""
+    S = oracle_binding.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    t0 = time.time()
+    _, cnt = S.march(sc["W"], sc["H"], row_begin=0, row_stride=rows_step, row_block=1)
+    dt = time.time() - t0
+    rows = cnt[::rows_step]
+    npx = rows.shape[0] * rows.shape[1]
+    return {"Q": float(rows[..., 1].mean() + 2.0 * rows[..., 2].mean()), "trips": float(rows[..., 0].mean()),
+            "lit": float(rows[..., 3].mean()), "pixels": npx, "seconds": dt}
+
+
+def run_reference(args):
+    """CPU arm: the reference's GLSL cannot be built here (no glslang / Vulkan / lavapipe), so this times the
+    oracle PORT of compute-clouds.comp on all host cores, on a bounded row sample of the same frame."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import _pkg
+    import oracle_binding as ob
+    import scenes
+    mm = _pkg.load_package()
+    assets = scenes.load_assets()
+    sc = scenes.make_scene(mm, args.config, assets)
+    cores = os.cpu_count()
+    rows_step = max(1, int(sc["W"] * sc["H"] / 150e3))     # ~150k pixels per step
+    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    times = []
+    npx = len(range(0, sc["H"], rows_step)) * sc["W"]
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        S.march(sc["W"], sc["H"], row_begin=0, row_stride=rows_step, row_block=1, counters=False)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    v = npx / dt / 1e6
+    sample = f"every {rows_step}th row of the {sc['W']}x{sc['H']} {args.config} frame ({npx} px per step), OpenMP over rows"
+    print(json.dumps({
+        "impl": "reference", "metric": "cloud-march throughput", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_full_frame_extrapolated": sc["W"] * sc["H"] / v / 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} {sc['W']}x{sc['H']} full-resolution cloud march, shipped textures"},
+        "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle port of compute-clouds.comp; stands in for the reference shader on lavapipe, which cannot run here"},
+        "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import _pkg
+    import scenes
+    mm = _pkg.load_package()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the cloud pass has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    assets = scenes.load_assets()
+    sc = scenes.make_scene(mm, args.config, assets)
+    W, H = sc["W"], sc["H"]
+    fmode = {"exact": mm.MM_FILTER_EXACT, "hw": mm.MM_FILTER_HW, "hybrid": mm.MM_FILTER_HYBRID}[args.filter]
+
+    cs = mm.ComputeShader(local, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+    cs.setFilterMode(fmode)
+    cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+
+    # output image lives on rank 0; other ranks map it through CUDA IPC and store into it over NVLink
+    from project_marshmallow_b200 import multigpu
+    shared = multigpu.SharedFrame(cs, rank, world, dist if world > 1 else None)
+
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    K, Wm = args.steps, args.warmup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def frame_once(ev0=None, ev1=None):
+        flush.fill_(1)                      # L2 flush between frames (outside the event pair)
+        if ev0 is not None:
+            ev0.record(stream)
+        cs.dispatch(mm.MM_FULL, rank, world, args.row_block if world > 1 else 1, stream=stream.cuda_stream)
+        if ev1 is not None:
+            ev1.record(stream)
+
+    for _ in range(Wm):
+        frame_once()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for i in range(K):
+        if world > 1:
+            barrier()                       # all ranks start each sharded frame together
+        frame_once(*evs[i])
+    barrier()
+    clocks = sampler.summary() if sampler else None
+    per = torch.tensor([a.elapsed_time(b) for a, b in evs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(per, op=dist.ReduceOp.MAX)      # frame time = slowest rank
+    ms = float(per.mean())
+    mpix = W * H / ms / 1e3
+
+    # ---- e2e: the call a user makes with HOST buffers (uniforms in, image out), pinned host memory
+    e2e = None
+    if world == 1:
+        host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+        hnp = host.numpy()
+        for _ in range(2):
+            cs.renderToHost(sc["cam"], sc["sky"], sc["sun"], out=hnp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(3, K // 2)
+        for _ in range(n_e2e):
+            cs.renderToHost(sc["cam"], sc["sky"], sc["sun"], out=hnp)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": W * H / dt / 1e6, "unit": "Mpix/s", "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": 328,
+               "d2h_bytes_per_step": W * H * 16, "note": "mm_render_to_host: uniform blocks from host, RGBA32F frame back to pinned host memory"}
+
+    if rank == 0:
+        peaks, which = measured_peaks()
+        import oracle_binding as ob
+        out = {
+            "metric": "cloud-march throughput", "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms, "ms_per_frame": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config} {W}x{H} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
+                       "filter": args.filter, "l2": "flushed (256 MB write between frames)", "parallelism": f"row-cyclic x{world}, row block {args.row_block}" if world > 1 else "single GPU"},
+            "clocks": clocks, "gpu_launches": K, "e2e": e2e,
+        }
+        if not args.no_cpu_baseline:
+            rows_step = max(1, int(W * H / 300e3))
+            wq = workload_Q(ob, sc, rows_step)
+            texpeak = N_SM * TEXPEAK_QUADS_PER_CLK_PER_SM * peaks["sm_max_mhz"] * 1e6
+            achieved = wq["Q"] * W * H / (ms * 1e-3)
+            out["roofline"] = {"bound": "tex", "achieved": achieved / 1e9, "peak": texpeak / 1e9, "unit": "Gquad/s", "frac": achieved / texpeak,
+                               "traffic": None, "Q_quads_per_pixel": wq["Q"], "loop_trips_per_pixel": wq["trips"], "lit_steps_per_pixel": wq["lit"],
+                               "peak_source": f"148 SM x 4 bilinear quads/clk x sm_max_mhz ({which} clock); algorithmic quads from the oracle's fetch counters",
+                               "hbm_floor_ms": W * H * 16 / (peaks["hbm_gbs"] * 1e9) * 1e3}
+            v = wq["pixels"] / wq["seconds"] / 1e6
+            out["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"every {rows_step}th row of the same frame ({wq['pixels']} px), oracle port with counters, OpenMP"}
+        print(json.dumps(out))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+    shared.close()
+    cs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,148 @@
+/*
+ * marshmallow.h -- C-ABI of the B200-native cloud ray-march pass and noise-texture build.
+ *
+ * This is the drop-in boundary for ONE path of mccannd/Project-Marshmallow: the compute dispatch of
+ * SkyEngine/SkyEngine/Shaders/compute-clouds.comp and the textures it samples.  Each entry point
+ * names the reference interface it replaces (paths relative to /root/reference/SkyEngine/SkyEngine).
+ * Plain C types only: opaque handle, pointers, sizes, int status (0 = MM_OK, negative = error;
+ * the reference throws std::runtime_error instead, main.cpp:8-14).  No exceptions cross this
+ * boundary.  One context per GPU; a context is not thread-safe (the reference is single-threaded).
+ * There is NO CPU fallback: every compute entry fails with MM_ERR_CUDA when no sm_100 device is
+ * usable.
+ */
+#ifndef MARSHMALLOW_H
+#define MARSHMALLOW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MM_API __attribute__((visibility("default")))
+
+typedef struct mm_ctx mm_ctx;
+
+enum mm_status {
+    MM_OK = 0,
+    MM_ERR_ARG = -1,        /* null / out-of-range argument */
+    MM_ERR_CUDA = -2,       /* CUDA runtime error or no usable device; see mm_last_error */
+    MM_ERR_STATE = -3,      /* a required texture / uniform / output was never bound */
+    MM_ERR_UNSUPPORTED = -4
+};
+
+/* texture slots = the sampler bindings of compute-clouds.comp:43-47 (set 2, bindings 4..8) */
+enum mm_tex_slot {
+    MM_TEX_PLACEMENT = 0,   /* binding 4 cloudPlacement   (VulkanApplication.cpp:253-254) */
+    MM_TEX_NIGHTSKY = 1,    /* binding 5 nightSkyMap      (VulkanApplication.cpp:255-256) */
+    MM_TEX_CURL = 2,        /* binding 6 curlNoise        (VulkanApplication.cpp:257-258) */
+    MM_TEX_LOWRES = 3,      /* binding 7 lowResCloudShape (VulkanApplication.cpp:259-260) */
+    MM_TEX_HIRES = 4        /* binding 8 hiResCloudShape  (VulkanApplication.cpp:261-262) */
+};
+
+/* which pixels one dispatch marches */
+enum mm_dispatch_mode {
+    MM_FULL = 0,            /* every pixel: the union of the reference's 16 phase dispatches */
+    MM_PHASE16 = 1          /* one reference dispatch: pixels (4*gx + o%4, 4*gy + o/4), o = int(sun.color.a)
+                               (compute-clouds.comp:291-301, VulkanApplication.cpp:1067-1071) */
+};
+
+/* sampler arithmetic (see DESIGN.md "sampler modes") */
+enum mm_filter_mode {
+    MM_FILTER_EXACT = 0,    /* FP32 software filtering, bit-identical to the CPU oracle (parity grade) */
+    MM_FILTER_HW = 1,       /* cudaTextureObject hardware filtering (8-bit weights), every fetch */
+    MM_FILTER_HYBRID = 2    /* march decisions: EXACT; the 6 light-cone samples: hardware filtering */
+};
+
+/* ---- context: replaces ComputeShader's constructor/destructor (Shader.h:338-353, Shader.cpp:633-645) */
+MM_API int mm_create(int device, mm_ctx **out);
+MM_API int mm_destroy(mm_ctx *ctx);
+MM_API const char *mm_last_error(const mm_ctx *ctx);        /* never NULL; ctx may be NULL for create errors */
+MM_API const char *mm_version(void);
+
+/* ---- textures: replace Texture::initFromFile / Texture3D::initFromFile + sampler creation
+ *      (Texture.cpp:212-246, 502-538; samplers Texture.cpp:29-52, 315-338: LINEAR, REPEAT, 1 mip).
+ *      rgba8 is HOST memory, RGBA8_UNORM, x fastest, then y, then z ([z][y][x][4]). */
+MM_API int mm_upload_tex2d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h);
+MM_API int mm_upload_tex3d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h, int d);
+
+/* ---- noise-texture build on the GPU.
+ * mm_build_curl_noise replaces the offline GenerateCurlNoise (ImageUtils.cpp:176-223): builds the
+ * 128x128 RGBA8 curl-noise FBM, binds it to MM_TEX_CURL, and optionally copies it to host memory.
+ * mm_build_noise_volumes builds the 128^3 Perlin-Worley/Worley-FBM and 32^3 Worley-FBM volumes the
+ * reference ships as Houdini-baked TGA slices (no reference generator exists), binds them to
+ * MM_TEX_LOWRES / MM_TEX_HIRES, and optionally copies them out ([z][y][x][4] bytes). */
+MM_API int mm_build_curl_noise(mm_ctx *ctx, uint8_t *out_rgba8_128x128_or_null);
+MM_API int mm_build_noise_volumes(mm_ctx *ctx, uint64_t seed, uint8_t *out_low128_or_null, uint8_t *out_hi32_or_null);
+
+/* ---- uniforms: replaces ComputeShader::updateUniformBuffers (Shader.cpp:967-992).  The four blocks
+ * are byte-identical to the reference structs: UniformCameraObject 160 B (Shader.h:24-29; view@0
+ * proj@64 cameraPosition@128 cameraParams@144), UniformSunObject 116 B (SkyManager.h:8-14; location@0
+ * direction@16 color@32 directionBasis@48 intensity@112), UniformSkyObject 52 B (SkyManager.h:28-36;
+ * betaR@0 betaV@16 wind@32 mie_directional@48).  camera_prev may be NULL (unused by the march). */
+MM_API int mm_set_uniforms(mm_ctx *ctx, const void *camera160, const void *camera_prev160_or_null,
+                           const void *sun116, const void *sky52);
+
+/* ---- output image: replaces descriptor set 0 (resultImage, rgba32f; VulkanApplication.cpp:247-250).
+ * mm_bind_output_linear: a DEVICE pointer to pitch-linear float4 pixels (pitch in bytes, >= 16*w).
+ *   The pointer may be peer memory of another GPU (multi-GPU gather is fused into the stores).
+ * mm_bind_output_external_fd: a VkImage's exported opaque-fd memory (R32G32B32A32_SFLOAT, optimal
+ *   tiling) imported with cudaImportExternalMemory -> mipmapped array -> surface object.
+ *   Compile-checked only in this environment (no Vulkan loader exists here).
+ * mm_alloc_output: convenience, allocates the image inside the context. */
+MM_API int mm_bind_output_linear(mm_ctx *ctx, float *dptr_rgba32f, size_t pitch_bytes, int w, int h);
+MM_API int mm_bind_output_external_fd(mm_ctx *ctx, int opaque_fd, size_t alloc_bytes, int w, int h);
+MM_API int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *pitch_out);
+
+/* ---- dispatch: replaces bindShader + vkCmdDispatch + vkQueueSubmit (Shader.h:358-376,
+ * VulkanApplication.cpp:1062-1071, 168-177).  Asynchronous on `stream` (a cudaStream_t, or NULL for
+ * the context's own stream).  Rows are partitioned in blocks of row_block rows; this call marches
+ * block b when (b - row_begin) % row_stride == 0 and b >= row_begin (single GPU: 0,1,1). */
+MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
+MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
+MM_API int mm_synchronize(mm_ctx *ctx);
+
+/* host-buffer convenience (the end-to-end call): uniforms in, march, image out to HOST memory.
+ * out_host: w*h*4 floats (packed).  Includes H2D of the uniforms and D2H of the image. */
+MM_API int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, const void *sky52,
+                             int mode, float *out_host_rgba32f);
+
+/* ---- HDR -> RGBA8 (tonemap.frag:11-28, vignette omitted) of the bound output; device or host dst */
+MM_API int mm_tonemap_rgba8(mm_ctx *ctx, uint8_t *dst, int dst_is_device, void *stream);
+
+/* ---- diagnostics: per-pixel work counters {loop trips, 2D fetches, 3D fetches, lit steps}
+ * (uint32 x4 per pixel, device memory owned by the context; NULL disables).  Algorithmic counts:
+ * what compute-clouds.comp would execute, whether or not the kernel skipped the work. */
+MM_API int mm_enable_counters(mm_ctx *ctx, int enable);
+MM_API int mm_read_counters(mm_ctx *ctx, uint32_t *host_out /* w*h*4 */);
+MM_API int mm_read_output(mm_ctx *ctx, float *host_out /* w*h*4 packed */);
+MM_API int mm_last_kernel_ms(mm_ctx *ctx, float *ms);       /* CUDA-event time of the last mm_dispatch */
+
+/* sampler probe: filters `n` coordinates (u,v,w triples) of a slot with the given mode on the GPU */
+MM_API int mm_sample(mm_ctx *ctx, int slot, int filter_mode, const float *uvw_host, int n, float *out_rgba_host);
+/* the deterministic pow of the decision path, evaluated on the GPU (bit-exactness probe) */
+MM_API int mm_det_pow(mm_ctx *ctx, const float *x_host, const float *y_host, int n, float *out_host);
+
+/* ---- multi-GPU plumbing (new work: the reference is single-device, VulkanApplication.cpp:639-687).
+ * One process per GPU.  Rank 0 exports the allocation behind its output image as a 64-byte CUDA-IPC
+ * handle; the other ranks open it and bind the mapped pointer with mm_bind_output_linear, so their
+ * march kernels store finished pixels straight into rank 0's image over NVLink (no gather step).
+ * dptr must be the base of an allocation made by mm_alloc_output. */
+MM_API int mm_ipc_get_handle(mm_ctx *ctx, void *dptr, uint8_t handle_out[64]);
+MM_API int mm_ipc_open_handle(mm_ctx *ctx, const uint8_t handle[64], void **dptr_out);
+MM_API int mm_ipc_close_handle(mm_ctx *ctx, void *dptr);
+
+/* ---- host-side value producers (CPU only; no device needed).  Restate the reference's
+ * SkyManager (SkyManager.cpp:15-70) and Camera (camera.cpp:27-39,179-195; camera.h:72) so that a
+ * caller without the engine can fill the uniform blocks exactly as VulkanApplication.cpp:351-386. */
+MM_API int mm_host_sky(float elevation, float azimuth, float turbidity, float rayleigh, float mie,
+                       float mie_directional, const float wind_xyz[3], float time, int pixel_phase,
+                       void *sun116_out, void *sky52_out);
+MM_API int mm_host_camera(const float position[3], float yaw, float pitch, float fov_deg, float aspect,
+                          void *camera160_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARSHMALLOW_H */

@@ -1,0 +1,668 @@
+/*
+ * cloud_march_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A float32 restatement, in plain C, of the reference's cloud ray-march compute pass
+ *     /root/reference/SkyEngine/SkyEngine/Shaders/compute-clouds.comp          ("CC")
+ * with the sampler semantics the reference configures in
+ *     /root/reference/SkyEngine/SkyEngine/Texture.cpp:29-52,315-338            (LINEAR, REPEAT, 1 mip)
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this file's shared object.  The shipped library (csrc/) never links or calls it.
+ *
+ * PARITY STATUS: "parity unpinned by the reference" for the march -- the reference has no tests,
+ * golden frames or runnable build for this path in this environment (no Vulkan loader, glslang or
+ * lavapipe).  The restatement is pinned only by (i) helper-level known
+ * answers derived by hand from the GLSL (tests/test_oracle_helpers.py) and (ii) the quirk
+ * register of SURVEY.md section 7 (Q1..Q14), each reproduced below and marked "Qn".
+ *
+ * Arithmetic contract (what "bit-exact decision path" means for the CUDA kernel):
+ *   - every expression is evaluated in IEEE binary32, in the order written in the GLSL, one
+ *     rounding per operator, NO fused multiply-add contraction (build: -ffp-contract=off);
+ *   - GLSL built-ins are defined as:  dot = ((ax*bx)+(ay*by))+(az*bz);  length = sqrt(dot(v,v));
+ *     normalize(v) = v * (1/sqrt(dot(v,v)));  mix(x,y,a) = x*(1-a) + y*a;
+ *     max(x,y) = (x<y)?y:x;  min(x,y) = (y<x)?y:x;  clamp(x,lo,hi): r = (x>lo)?x:lo; (r<hi)?r:hi
+ *     (NaN -> lo, Q6);
+ *     smoothstep(e0,e1,x): t = clamp((x-e0)/(e1-e0),0,1); t*t*(3-2*t);
+ *   - the texture unit is restated as: texel = byte/255.0f (IEEE divide), unnormalised coordinate
+ *     U = u*N - 0.5f, i0 = floor(U), weight a = U - i0, REPEAT wrap, and three (two) nested
+ *     lerps  lerp(p,q,a) = fmaf(a, q-p, p)  in x, then y, then z  (filter mode OM_FILTER_FP32).
+ *     OM_FILTER_FIX8 rounds each weight to 8 fractional bits first (what NVIDIA texture units do,
+ *     CUDA C Programming Guide "Linear Filtering"); it exists to measure how sensitive the march
+ *     is to sampler precision, not as a second truth;
+ *   - the one transcendental that feeds a branch, pow() in heightBiasCoverage (CC:206-208), is
+ *     computed by om_det_powf(): a fixed sequence of IEEE binary64 +,-,*,/ operations (no libm),
+ *     so that a GPU can reproduce it bit for bit.  exp/pow/acos/cos in shading (CC:88-127,
+ *     CC:456-462, CC:490) use libm; they are smooth and never thresholded.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "oracle.h"
+
+/* ------------------------------------------------------------------------------------------ */
+/* small vector helpers                                                                         */
+typedef struct { float x, y, z; } v3;
+
+static inline v3 V3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 add3(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 sub3(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 mul3(v3 a, v3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 div3(v3 a, v3 b) { return V3(a.x / b.x, a.y / b.y, a.z / b.z); }
+static inline v3 scale3(float s, v3 a) { return V3(s * a.x, s * a.y, s * a.z); }
+static inline float dot3(v3 a, v3 b) { return ((a.x * b.x) + (a.y * b.y)) + (a.z * b.z); }
+static inline float length3(v3 a) { return sqrtf(dot3(a, a)); }
+static inline v3 normalize3(v3 a) { float inv = 1.0f / sqrtf(dot3(a, a)); return V3(a.x * inv, a.y * inv, a.z * inv); }
+/* GLSL max/min as the spec writes them; clamp sends NaN to lo (Q6) and -0 to +0 when lo == 0 */
+static inline float omaxf(float x, float y) { return (x < y) ? y : x; }
+static inline float ominf(float x, float y) { return (y < x) ? y : x; }
+static inline float clampf(float x, float lo, float hi) { float r = (x > lo) ? x : lo; return (r < hi) ? r : hi; }
+static inline float mixf(float x, float y, float a) { return (x * (1.0f - a)) + (y * a); }
+static inline float smoothstepf(float e0, float e1, float x) {
+    float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f);
+    return (t * t) * (3.0f - (2.0f * t));
+}
+
+/* CC:65-71 */
+static inline float remapf(float value, float oldMin, float oldMax, float newMin, float newMax) {
+    return newMin + (((value - oldMin) / (oldMax - oldMin)) * (newMax - newMin));
+}
+static inline float remapClampedf(float value, float oldMin, float oldMax, float newMin, float newMax) {
+    return clampf(newMin + (((value - oldMin) / (oldMax - oldMin)) * (newMax - newMin)), newMin, newMax);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* deterministic pow for the decision path (see header).  Domain: x >= 0, 0 < y <= 8.           */
+float om_det_powf(float x, float y) {
+    if (y == 1.0f) return x;
+    if (!(x > 0.0f)) return 0.0f;               /* pow(0, y>0) = 0; negative/NaN base -> 0 (GLSL: undefined) */
+    if (x == 1.0f) return 1.0f;
+    double dx = (double)x;
+    uint64_t bits; memcpy(&bits, &dx, 8);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    bits = (bits & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL;
+    double m; memcpy(&m, &bits, 8);              /* m in [1,2) */
+    if (m > 1.4142135623730951) { m = m * 0.5; e = e + 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    /* log2(m) = (2/ln2) * s * (1 + s2/3 + s2^2/5 + ... ), |s| <= 0.1716 */
+    double p = 1.0 / 21.0;
+    p = p * s2 + 1.0 / 19.0;
+    p = p * s2 + 1.0 / 17.0;
+    p = p * s2 + 1.0 / 15.0;
+    p = p * s2 + 1.0 / 13.0;
+    p = p * s2 + 1.0 / 11.0;
+    p = p * s2 + 1.0 / 9.0;
+    p = p * s2 + 1.0 / 7.0;
+    p = p * s2 + 1.0 / 5.0;
+    p = p * s2 + 1.0 / 3.0;
+    p = p * s2 + 1.0;
+    double l = (double)e + (s * p) * 2.8853900817779268;    /* 2/ln(2) */
+    double t = (double)y * l;
+    double n = floor(t + 0.5);
+    double f = (t - n) * 0.6931471805599453;                 /* ln(2); |f| <= 0.3466 */
+    /* exp(f), Taylor to degree 13 */
+    double q = 1.0 / 6227020800.0;
+    q = q * f + 1.0 / 479001600.0;
+    q = q * f + 1.0 / 39916800.0;
+    q = q * f + 1.0 / 3628800.0;
+    q = q * f + 1.0 / 362880.0;
+    q = q * f + 1.0 / 40320.0;
+    q = q * f + 1.0 / 5040.0;
+    q = q * f + 1.0 / 720.0;
+    q = q * f + 1.0 / 120.0;
+    q = q * f + 1.0 / 24.0;
+    q = q * f + 1.0 / 6.0;
+    q = q * f + 0.5;
+    q = q * f + 1.0;
+    q = q * f + 1.0;
+    int ni = (int)n;
+    if (ni < -1000) return 0.0f;
+    uint64_t sb = (uint64_t)(ni + 1023) << 52;
+    double sc; memcpy(&sc, &sb, 8);
+    return (float)(q * sc);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* software sampler: Texture.cpp:29-52 (2D) and :315-338 (3D): LINEAR, REPEAT, LOD 0, RGBA8_UNORM */
+typedef struct {
+    const float *texels;  /* w*h*d*4 floats, byte/255.0f */
+    int w, h, d;
+} ftex;
+
+static inline int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+static inline float lerpf(float p, float q, float a) { return __builtin_fmaf(a, q - p, p); }
+
+static inline void filter_coord(float u, int n, int filter, int *i0, int *i1, float *a) {
+    float U = (u * (float)n) - 0.5f;
+    float fl = floorf(U);
+    float w = U - fl;
+    int i = (int)fl;
+    if (filter == OM_FILTER_FIX8) {
+        /* 1.8 fixed-point weight, round to nearest; a weight of 256/256 carries into the next texel */
+        float w8 = floorf((w * 256.0f) + 0.5f);
+        if (w8 >= 256.0f) { w8 = 0.0f; i = i + 1; }
+        w = w8 * (1.0f / 256.0f);
+    }
+    *i0 = wrapi(i, n);
+    *i1 = wrapi(*i0 + 1, n);
+    *a = w;
+}
+
+static void sample2d(const ftex *t, int filter, float u, float v, float out[4]) {
+    int x0, x1, y0, y1; float a, b;
+    filter_coord(u, t->w, filter, &x0, &x1, &a);
+    filter_coord(v, t->h, filter, &y0, &y1, &b);
+    const float *t00 = t->texels + 4 * ((size_t)y0 * t->w + x0);
+    const float *t10 = t->texels + 4 * ((size_t)y0 * t->w + x1);
+    const float *t01 = t->texels + 4 * ((size_t)y1 * t->w + x0);
+    const float *t11 = t->texels + 4 * ((size_t)y1 * t->w + x1);
+    for (int c = 0; c < 4; c++) {
+        float top = lerpf(t00[c], t10[c], a);
+        float bot = lerpf(t01[c], t11[c], a);
+        out[c] = lerpf(top, bot, b);
+    }
+}
+
+static void sample3d(const ftex *t, int filter, float u, float v, float w, float out[4]) {
+    int x0, x1, y0, y1, z0, z1; float a, b, g;
+    filter_coord(u, t->w, filter, &x0, &x1, &a);
+    filter_coord(v, t->h, filter, &y0, &y1, &b);
+    filter_coord(w, t->d, filter, &z0, &z1, &g);
+    size_t sy = (size_t)t->w, sz = (size_t)t->w * t->h;
+    const float *T = t->texels;
+    const float *t000 = T + 4 * (z0 * sz + y0 * sy + x0), *t100 = T + 4 * (z0 * sz + y0 * sy + x1);
+    const float *t010 = T + 4 * (z0 * sz + y1 * sy + x0), *t110 = T + 4 * (z0 * sz + y1 * sy + x1);
+    const float *t001 = T + 4 * (z1 * sz + y0 * sy + x0), *t101 = T + 4 * (z1 * sz + y0 * sy + x1);
+    const float *t011 = T + 4 * (z1 * sz + y1 * sy + x0), *t111 = T + 4 * (z1 * sz + y1 * sy + x1);
+    for (int c = 0; c < 4; c++) {
+        float x00 = lerpf(t000[c], t100[c], a);
+        float x10 = lerpf(t010[c], t110[c], a);
+        float x01 = lerpf(t001[c], t101[c], a);
+        float x11 = lerpf(t011[c], t111[c], a);
+        float y0v = lerpf(x00, x10, b);
+        float y1v = lerpf(x01, x11, b);
+        out[c] = lerpf(y0v, y1v, g);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+struct om_scene {
+    ftex placement, nightsky, curl, lowres, hires;
+    float *store[5];
+    float cam[40];   /* UniformCameraObject, 160 B: Shader.h:24-29 */
+    float sun[29];   /* UniformSunObject,    116 B: SkyManager.h:8-14 */
+    float sky[13];   /* UniformSkyObject,     52 B: SkyManager.h:28-36 */
+    int filter;      /* OM_FILTER_* */
+    int pow_mode;    /* OM_POW_*    */
+};
+
+typedef struct { uint32_t trips, n2d, n3d, lit; } px_counters;
+
+typedef struct {
+    const struct om_scene *s;
+    v3 cameraPos, earthCenter, windXYZ;
+    float timeOffset;
+    px_counters *cnt;
+} ctx_t;
+
+om_scene *om_scene_create(void) {
+    om_scene *s = (om_scene *)calloc(1, sizeof(om_scene));
+    return s;
+}
+void om_scene_destroy(om_scene *s) {
+    if (!s) return;
+    for (int i = 0; i < 5; i++) free(s->store[i]);
+    free(s);
+}
+int om_scene_set_texture(om_scene *s, int slot, const uint8_t *rgba8, int w, int h, int d) {
+    if (!s || slot < 0 || slot > 4 || !rgba8 || w <= 0 || h <= 0 || d <= 0) return -1;
+    size_t n = (size_t)w * h * d * 4;
+    float *f = (float *)malloc(n * sizeof(float));
+    if (!f) return -2;
+    for (size_t i = 0; i < n; i++) f[i] = (float)rgba8[i] / 255.0f;   /* UNORM8 -> float */
+    free(s->store[slot]);
+    s->store[slot] = f;
+    ftex t = {f, w, h, d};
+    switch (slot) {
+        case OM_TEX_PLACEMENT: s->placement = t; break;
+        case OM_TEX_NIGHTSKY:  s->nightsky = t; break;
+        case OM_TEX_CURL:      s->curl = t; break;
+        case OM_TEX_LOWRES:    s->lowres = t; break;
+        case OM_TEX_HIRES:     s->hires = t; break;
+    }
+    return 0;
+}
+int om_scene_set_uniforms(om_scene *s, const void *camera160, const void *sun116, const void *sky52) {
+    if (!s || !camera160 || !sun116 || !sky52) return -1;
+    memcpy(s->cam, camera160, 160);
+    memcpy(s->sun, sun116, 116);
+    memcpy(s->sky, sky52, 52);
+    return 0;
+}
+int om_scene_set_modes(om_scene *s, int filter, int pow_mode) {
+    if (!s) return -1;
+    s->filter = filter; s->pow_mode = pow_mode;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+#define ATMOSPHERE_RADIUS 2000000.0f                       /* CC:56 */
+#define ONE_OVER_FOURPI 0.07957747154594767f               /* CC:63 */
+#define THREE_OVER_SIXTEENPI 0.05968310365946075f          /* CC:62 */
+#define SUN_ANGULAR_COS 0.999956676946448443553574619906976478926848692873900859324f  /* CC:82 */
+#define PI_F 3.14159265f                                   /* CC:59 */
+#define WIND_STRENGTH 20.0f                                /* CC:279 */
+#define MAX_STEPS 100                                      /* CC:286 */
+
+/* CC:73-77 */
+static float hgPhase(float cosTheta, float g) {
+    float g2 = g * g;
+    float inv = 1.0f / powf(((1.0f - ((2.0f * g) * cosTheta)) + g2), 1.5f);
+    return ONE_OVER_FOURPI * ((1.0f - g2) * inv);
+}
+float om_hgPhase(float c, float g) { return hgPhase(c, g); }
+
+/* CC:84-86 */
+static float rayleighPhase(float cosTheta) { return THREE_OVER_SIXTEENPI * (1.0f + (cosTheta * cosTheta)); }
+
+/* CC:88-127 (Q11: sunDisk forced to 0; fex sign as written) */
+static v3 getAtmosphereColorPhysical(const struct om_scene *s, v3 dir, v3 sunDir) {
+    float sunE = s->sun[28];
+    v3 BetaR = V3(s->sky[0], s->sky[1], s->sky[2]);
+    v3 BetaM = V3(s->sky[4], s->sky[5], s->sky[6]);
+
+    float zenith = acosf(omaxf(0.0f, dir.y));
+    float inverse = 1.0f / (cosf(zenith) + (0.15f * powf(93.885f - ((zenith * 180.0f) / PI_F), -1.253f)));
+    float sR = 8.4E3f * inverse;
+    float sM = 1.25E3f * inverse;
+
+    v3 ex = add3(scale3(sR, V3(-BetaR.x, -BetaR.y, -BetaR.z)), scale3(sM, BetaM));
+    v3 fex = V3(expf(ex.x), expf(ex.y), expf(ex.z));
+
+    float cosTheta = dot3(sunDir, dir);
+    float rPhase = rayleighPhase((cosTheta * 0.5f) + 0.5f);
+    v3 betaRTheta = scale3(rPhase, BetaR);
+    float mPhase = hgPhase(cosTheta, s->sky[12]);
+    v3 betaMTheta = scale3(mPhase, BetaM);
+
+    float yDot = 1.0f - sunDir.y;
+    yDot *= (((yDot * yDot) * yDot) * yDot);
+    v3 betas = div3(add3(betaRTheta, betaMTheta), add3(BetaR, BetaM));
+    v3 a = mul3(scale3(sunE, betas), V3(1.0f - fex.x, 1.0f - fex.y, 1.0f - fex.z));
+    v3 Lin = V3(powf(a.x, 1.5f), powf(a.y, 1.5f), powf(a.z, 1.5f));
+    v3 b = mul3(scale3(sunE, betas), fex);
+    float yc = clampf(yDot, 0.0f, 1.0f);
+    Lin = mul3(Lin, V3(mixf(1.0f, powf(b.x, 0.5f), yc), mixf(1.0f, powf(b.y, 0.5f), yc), mixf(1.0f, powf(b.z, 0.5f), yc)));
+
+    v3 L0 = scale3(0.1f, fex);
+    float sunDisk = 0.0f;                                                     /* CC:119-120 */
+    L0 = add3(L0, scale3(sunDisk, scale3(sunE * 15000.0f, fex)));             /* CC:121 */
+
+    v3 color = add3(scale3(0.04f, add3(Lin, L0)), V3(0.0f, 0.0003f, 0.00075f));
+    return color;
+}
+
+/* CC:147-177.  Q1: .t is measured from the translated+scaled origin.  Returns valid flag. */
+static int raySphereIntersection(v3 ro, v3 rd, v3 c, float w, float *t_out) {
+    ro = sub3(ro, c);
+    ro = V3(ro.x / w, ro.y / w, ro.z / w);
+    float A = dot3(rd, rd);
+    float B = 2.0f * dot3(rd, ro);
+    float C = dot3(ro, ro) - 0.25f;
+    float discriminant = (B * B) - ((4.0f * A) * C);
+    *t_out = 0.0f;                       /* GLSL leaves isect.t undefined on a miss; defined as 0 here and in the kernel */
+    if (discriminant < 0.0f) return 0;
+    float t = (((-sqrtf(discriminant)) - B) / A) * 0.5f;
+    if (t < 0.0f) t = ((sqrtf(discriminant) - B) / A) * 0.5f;
+    if (t >= 0.0f) {
+        v3 p = add3(ro, scale3(t, rd));
+        p = scale3(w, p);
+        p = add3(p, c);
+        *t_out = length3(sub3(p, ro));
+        return 1;
+    }
+    return 0;
+}
+int om_raySphereIntersection(const float ro[3], const float rd[3], const float sphere[4], float *t) {
+    return raySphereIntersection(V3(ro[0], ro[1], ro[2]), V3(rd[0], rd[1], rd[2]), V3(sphere[0], sphere[1], sphere[2]), sphere[3], t);
+}
+
+/* CC:180-188 */
+static inline v3 getProjectedShellPoint(v3 pt, v3 center) {
+    return add3(scale3(0.5f * ATMOSPHERE_RADIUS, normalize3(sub3(pt, center))), center);
+}
+static inline float getRelativeHeight(v3 pt, v3 projectedPt, float thickness) {
+    return clampf(length3(sub3(pt, projectedPt)) / thickness, 0.0f, 1.0f);
+}
+
+/* CC:193-204 */
+static float cloudLayerDensity(float relativeHeight, float cloudType) {
+    relativeHeight = clampf(relativeHeight, 0.0f, 1.0f);
+    float cumulus = omaxf(0.0f, remapf(relativeHeight, 0.0f, 0.2f, 0.0f, 1.0f) * remapf(relativeHeight, 0.7f, 0.9f, 1.0f, 0.0f));
+    float stratocumulus = omaxf(0.0f, remapf(relativeHeight, 0.0f, 0.2f, 0.0f, 1.0f) * remapf(relativeHeight, 0.2f, 0.7f, 1.0f, 0.0f));
+    float stratus = omaxf(0.0f, remapf(relativeHeight, 0.0f, 0.1f, 0.0f, 1.0f) * remapf(relativeHeight, 0.2f, 0.3f, 1.0f, 0.0f));
+    float d1 = mixf(stratus, stratocumulus, clampf(cloudType * 2.0f, 0.0f, 1.0f));
+    float d2 = mixf(stratocumulus, cumulus, clampf((cloudType - 0.5f) * 2.0f, 0.0f, 1.0f));
+    return mixf(d1, d2, cloudType);
+}
+float om_cloudLayerDensity(float h, float t) { return cloudLayerDensity(h, t); }
+
+/* CC:206-208 */
+static float heightBiasCoverage(const struct om_scene *s, float coverage, float height) {
+    float k = clampf(remapf(height, 0.7f, 0.8f, 1.0f, 0.8f), 0.8f, 1.0f);
+    return s->pow_mode == OM_POW_LIBM ? powf(coverage, k) : om_det_powf(coverage, k);
+}
+float om_heightBiasCoverage(float coverage, float height) {
+    struct om_scene s; memset(&s, 0, sizeof s);
+    return heightBiasCoverage(&s, coverage, height);
+}
+float om_remap(float v, float a, float b, float c, float d) { return remapf(v, a, b, c, d); }
+float om_remapClamped(float v, float a, float b, float c, float d) { return remapClampedf(v, a, b, c, d); }
+
+/* CC:214-228 */
+static float cloudHiRes(const ctx_t *cx, v3 pos, float curlStrength, float origDensity, float relativeHeight) {
+    const struct om_scene *s = cx->s;
+    float c = 0.0001f;
+    float cu[4];
+    sample2d(&s->curl, s->filter, c * pos.x, c * pos.z, cu);
+    cx->cnt->n2d++;
+    v3 curl = V3((2.0f * cu[0]) - 1.0f, (2.0f * cu[1]) - 1.0f, (2.0f * cu[2]) - 1.0f);
+    pos = add3(pos, scale3(1.9f * curlStrength, curl));
+
+    float dn[4];
+    sample3d(&s->hires, s->filter, 0.0004f * pos.x, 0.0004f * pos.y, 0.0004f * pos.z, dn);
+    cx->cnt->n3d++;
+    float erosion = ((0.625f * dn[0]) + (0.25f * dn[1])) + (0.125f * dn[2]);
+    erosion = mixf(erosion, 1.0f - erosion, clampf(relativeHeight * 10.0f, 0.0f, 1.0f));
+    return remapClampedf(origDensity, 1.0f * erosion, 1.0f, 0.0f, 1.0f);
+}
+
+/* CC:231-253 (Q2: heightBiasCoverage called with swapped arguments) */
+static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
+    const struct om_scene *s = cx->s;
+    v3 currentProj = getProjectedShellPoint(pos, cx->earthCenter);
+    float ci[4];
+    sample2d(&s->placement, s->filter, 0.000009f * (currentProj.x - cx->cameraPos.x), 0.000009f * (currentProj.z - cx->cameraPos.z), ci);
+    cx->cnt->n2d++;
+    float layerDensity = cloudLayerDensity(relativeHeight, ci[2]);
+    float dn[4];
+    sample3d(&s->lowres, s->filter, 0.00002f * pos.x, 0.00002f * pos.y, 0.00002f * pos.z, dn);
+    cx->cnt->n3d++;
+
+    float density = layerDensity * remapClampedf(dn[0], 0.3f, 1.0f, 0.0f, 1.0f);
+    if (density < 0.0001f) return 0.0f;
+
+    float coverage = heightBiasCoverage(s, relativeHeight, ominf(0.85f, ci[0]));
+
+    float erosion = ((0.625f * dn[1]) + (0.25f * dn[2])) + (0.125f * dn[3]);
+    erosion = remapClampedf(erosion, coverage, 1.0f, 0.0f, 1.0f);
+    density = remapClampedf(density, erosion, 1.0f, 0.0f, 1.0f);
+    return density;
+}
+
+/* CC:256-277 */
+static void fromAngleAxis(v3 angle, float angleRad, float rot[9]) {
+    float cost = cosf(angleRad), sint = sinf(angleRad);
+    rot[0] = cost + ((angle.x * angle.x) * (1.f - cost));
+    rot[1] = ((angle.y * angle.x) * (1.f - cost)) + (angle.z * sint);
+    rot[2] = ((angle.z * angle.x) * (1.f - cost)) - (angle.y * sint);
+    rot[3] = ((angle.x * angle.y) * (1.f - cost)) - (angle.z * sint);
+    rot[4] = cost + ((angle.y * angle.y) * (1.f - cost));
+    rot[5] = ((angle.z * angle.y) * (1.f - cost)) + (angle.x * sint);
+    rot[6] = ((angle.x * angle.z) * (1.f - cost)) + (angle.y * sint);
+    rot[7] = ((angle.y * angle.z) * (1.f - cost)) - (angle.x * sint);
+    rot[8] = cost + ((angle.z * angle.z) * (1.f - cost));
+}
+/* column-major mat3 * vec3: ((c0*v.x) + (c1*v.y)) + (c2*v.z) */
+static inline v3 mat3mul(const float m[9], v3 v) {
+    return V3(((m[0] * v.x) + (m[3] * v.y)) + (m[6] * v.z),
+              ((m[1] * v.x) + (m[4] * v.y)) + (m[7] * v.z),
+              ((m[2] * v.x) + (m[5] * v.y)) + (m[8] * v.z));
+}
+
+/* CC:288-500 for one target pixel.  W,H replace the hard-coded 1920x1080 (Q7, CC:283-285). */
+static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, float out[4], px_counters *cnt) {
+    ctx_t cx; cx.s = s; cx.cnt = cnt;
+    const float *cam = s->cam, *sun = s->sun, *sky = s->sky;
+    float timeOffset = sky[11];                                                   /* CC:289 */
+
+    float uvx = (float)px / (float)W, uvy = (float)py / (float)H;                 /* CC:305 */
+    float spx = (uvx * 2.0f) - 1.0f, spy = (uvy * 2.0f) - 1.0f;                   /* CC:309 */
+
+    v3 camLook = V3(cam[2], cam[6], cam[10]);                                     /* CC:312-314 */
+    v3 camRight = V3(cam[0], cam[4], cam[8]);
+    v3 camUp = V3(cam[1], cam[5], cam[9]);
+    v3 cameraPos = V3(cam[32], cam[33], cam[34]);                                 /* CC:317 */
+    float aspect = cam[36], tanH = cam[37];
+    v3 refPoint = sub3(cameraPos, camLook);
+    v3 p = sub3(add3(refPoint, scale3((aspect * spx) * tanH, camRight)), scale3(spy * tanH, camUp));  /* CC:320 */
+    v3 rayDirection = normalize3(sub3(p, cameraPos));                             /* CC:322 */
+
+    v3 sunDir = normalize3(V3(sun[16], sun[17], sun[18]));                        /* CC:324: directionBasis[1] */
+    float sunDirectionY = sun[5];
+
+    float dotToSun = omaxf(0.0f, dot3(sunDir, rayDirection));                     /* CC:326-340 */
+    float skyAmbient = dotToSun * 0.18f;
+    skyAmbient *= (skyAmbient * skyAmbient);
+    float sunDisk = smoothstepf(SUN_ANGULAR_COS, SUN_ANGULAR_COS + 0.00003f, dotToSun);
+    dotToSun *= ((dotToSun * dotToSun) * dotToSun);
+    dotToSun *= ((dotToSun * dotToSun) * dotToSun);
+    dotToSun *= ((dotToSun * dotToSun) * dotToSun);
+    dotToSun *= ((dotToSun * dotToSun) * dotToSun);
+    dotToSun *= (dotToSun * dotToSun);
+    if (sunDirectionY < 0.0f)
+        dotToSun *= (((((dotToSun * dotToSun) * dotToSun) * dotToSun) * dotToSun) * dotToSun);
+    sunDisk = omaxf(sunDisk, dotToSun);
+    sunDisk = omaxf(0.0f, sunDisk);
+
+    float fr = 0, fg = 0, fb = 0, fa = 0;                                         /* CC:342-348 */
+    v3 backgroundCol = V3(0, 0, 0);
+    if (sunDirectionY >= 0.0f) {
+        backgroundCol = getAtmosphereColorPhysical(s, rayDirection, sunDir);
+        fa = omaxf(skyAmbient, sunDisk);
+        fr = backgroundCol.x; fg = backgroundCol.y; fb = backgroundCol.z;
+    }
+
+    if (rayDirection.y < 0.0f) {                                                  /* CC:351-354 */
+        out[0] = fr; out[1] = fg; out[2] = fb; out[3] = fa;
+        return;
+    }
+
+    v3 earthCenter = V3(cameraPos.x, (-ATMOSPHERE_RADIUS * 0.5f) * 0.995f, cameraPos.z);   /* CC:357-358 */
+    float atmosphereThickness = (0.5f * ATMOSPHERE_RADIUS) * 0.02f;               /* CC:360 */
+    float tInner, tOuter;
+    raySphereIntersection(cameraPos, rayDirection, earthCenter, ATMOSPHERE_RADIUS, &tInner);          /* CC:362 */
+    raySphereIntersection(cameraPos, rayDirection, earthCenter, ATMOSPHERE_RADIUS * 1.02f, &tOuter);  /* CC:363 */
+    cx.cameraPos = cameraPos; cx.earthCenter = earthCenter;
+
+    if (sunDirectionY < 0.0f) {                                                   /* CC:365-384 (night; a14) */
+        float rot[9];
+        fromAngleAxis(normalize3(V3(1.0f, 0.0f, 1.0f)), sunDirectionY * 0.5f, rot);
+        v3 rotatedRayDir = mat3mul(rot, rayDirection);
+        v3 rotatedRayOrigin = mat3mul(rot, cameraPos);
+        v3 point = add3(scale3(tOuter, rotatedRayDir), rotatedRayOrigin);
+        v3 projectedPoint = getProjectedShellPoint(point, earthCenter);
+        float nu = (0.00002f * (projectedPoint.x - cameraPos.x)) + 0.35f;
+        float nv = (0.00002f * (projectedPoint.z - cameraPos.z)) + 0.35f;
+        float ns[4] = {0, 0, 0, 0};
+        if (s->nightsky.texels) { sample2d(&s->nightsky, s->filter, nu, nv, ns); cnt->n2d++; }
+        backgroundCol = V3(ns[0], ns[1], ns[2]);
+        backgroundCol = mul3(backgroundCol, scale3(0.75f, V3(sqrtf(backgroundCol.x), sqrtf(backgroundCol.y), sqrtf(backgroundCol.z))));
+        backgroundCol = V3(powf(backgroundCol.x, 2.2f), powf(backgroundCol.y, 2.2f), powf(backgroundCol.z, 2.2f));
+        backgroundCol = scale3(10.0f, backgroundCol);
+        float falloff = powf(rayDirection.y, 6.0f);
+        backgroundCol = scale3(falloff, backgroundCol);
+        float mt = powf(rayDirection.y, 0.03125f);
+        backgroundCol = V3(mixf(0.3f * 0.05f, backgroundCol.x, mt), mixf(0.6f * 0.05f, backgroundCol.y, mt), mixf(4.0f * 0.05f, backgroundCol.z, mt));
+        backgroundCol = add3(backgroundCol, V3(sunDisk, sunDisk, sunDisk));
+        fa = sunDisk;
+    }
+
+    float cosTheta = dot3(rayDirection, sunDir);                                  /* CC:386-390 */
+    float accumDensity = 0.0f;
+    float transmittance = 1.0f;
+    float stepSize = 0.05f * atmosphereThickness;
+
+    float basis[9] = {sun[12], sun[13], sun[14], sun[16], sun[17], sun[18], sun[20], sun[21], sun[22]};  /* mat3(directionBasis) CC:392 */
+    static const float sv[6][3] = {{0, 0.6f, 0}, {0, 0.5f, 0.05f}, {0.1f, 0.75f, 0}, {0.2f, 2.5f, 0.3f}, {0, 6, 0}, {-0.1f, 1, -0.2f}};
+    v3 samples[6];
+    for (int i = 0; i < 6; i++) samples[i] = mat3mul(basis, V3(sv[i][0], sv[i][1], sv[i][2]));        /* CC:393-401 */
+
+    int noHits = 1, misses = 0, steps = 0;                                        /* CC:403-405 */
+    v3 windXYZ = V3(sky[8], sky[9], sky[10]);
+
+    float henyeyGreenstein = omaxf(hgPhase(cosTheta, 0.6f), 0.7f * hgPhase(cosTheta, 0.99f - 0.1f));   /* CC:407 */
+    for (float t = tInner; t < tOuter; t += stepSize) {                           /* CC:408 */
+        cnt->trips++;
+        v3 currentPos = add3(cameraPos, scale3(t, rayDirection));
+        v3 currentProj = getProjectedShellPoint(currentPos, earthCenter);
+        float rHeight = getRelativeHeight(currentPos, currentProj, atmosphereThickness);
+        v3 windOffset = scale3((timeOffset + (rHeight * 200.0f)),
+                               scale3(WIND_STRENGTH, add3(windXYZ, scale3(rHeight, V3(0.1f, 0.05f, 0.0f)))));    /* CC:414 (Q8) */
+
+        float density = cloudTest(&cx, add3(currentPos, windOffset), rHeight);    /* CC:421 */
+        float loDensity = density;
+
+        if (density > 0.0f) {                                                     /* CC:426 */
+            misses = 0;
+            if (noHits) {                                                         /* CC:428-434 (Q3, Q4) */
+                t -= stepSize;
+                stepSize *= 0.3f;
+                noHits = 0;
+                continue;
+            }
+            density = cloudHiRes(&cx, add3(currentPos, windOffset), stepSize, density, rHeight);       /* CC:436 (Q9) */
+            if (density < 0.0001f) continue;                                      /* CC:437 (Q3) */
+            cnt->lit++;
+            float densityAlongLight = 0.0f;
+            for (int i = 0; i < 6; i++) {                                         /* CC:441-453 */
+                v3 lsPos = add3(currentPos, scale3(3.0f * stepSize, samples[i]));
+                v3 lsProj = getProjectedShellPoint(lsPos, earthCenter);
+                float lsHeight = getRelativeHeight(lsPos, lsProj, atmosphereThickness);
+                windOffset = scale3((timeOffset + (lsHeight * 200.0f)),
+                                    scale3(WIND_STRENGTH, add3(windXYZ, scale3(lsHeight, V3(0.1f, 0.05f, 0.0f)))));
+                float lsDensity = cloudTest(&cx, add3(lsPos, windOffset), lsHeight);
+                if (lsDensity > 0.0f) {
+                    lsDensity = cloudHiRes(&cx, add3(lsPos, windOffset), stepSize, lsDensity, lsHeight);
+                    densityAlongLight += lsDensity;
+                }
+            }
+            float beersLaw = expf(-densityAlongLight);                            /* CC:456-466 (Q10) */
+            float beersModulated = omaxf(beersLaw, 0.7f * expf(-0.25f * densityAlongLight));
+            beersLaw = mixf(beersLaw, beersModulated, ((-cosTheta) * 0.5f) + 0.5f);
+            float inScatter = 0.09f + powf(loDensity, remapClampedf(rHeight, 0.3f, 0.85f, 0.5f, 2.0f));
+            inScatter *= powf(remapClampedf(rHeight, 0.07f, 0.34f, 0.1f, 1.0f), 0.8f);
+            transmittance = mixf(transmittance, (inScatter * henyeyGreenstein) * beersLaw, (1.0f - accumDensity));
+            accumDensity += density;
+        } else if (!noHits) {                                                     /* CC:468-474 */
+            misses++;
+            if (misses >= 10) {
+                noHits = 1;
+                stepSize /= 0.3f;
+            }
+        }
+
+        if (accumDensity > 0.99f) {                                               /* CC:476-479 */
+            accumDensity = 1.0f;
+            break;
+        }
+        if (++steps > MAX_STEPS) break;                                           /* CC:481 (Q5) */
+    }
+
+    accumDensity *= smoothstepf(0.0f, 1.0f, ominf(1.0f, remapf(rayDirection.y, 0.0f, 0.1f, 0.0f, 1.0f)));  /* CC:485 */
+    accumDensity = ominf(accumDensity, 0.999f);                                   /* CC:486 */
+
+    v3 sunColor = V3(sun[8], sun[9], sun[10]);
+    float sunI = sun[28];
+    v3 cloudColor;
+    float e = expf(-transmittance);
+    float direct = sunI * omaxf(0.0f, transmittance);
+    if (sunDirectionY >= 0.0f) {                                                  /* CC:489-493 */
+        cloudColor = mul3(sunColor, add3(V3(direct, direct, direct), scale3(e, scale3(0.08f, backgroundCol))));
+    } else {
+        float pw = powf(rayDirection.y, 0.03125f);
+        v3 nightAmb = scale3(pw, scale3(0.05f, V3(0.3f, 0.6f, 4.0f)));
+        cloudColor = mul3(sunColor, add3(V3(direct, direct, direct), scale3(e, scale3(0.08f, nightAmb))));
+    }
+    out[0] = mixf(backgroundCol.x, cloudColor.x, accumDensity);                   /* CC:495 */
+    out[1] = mixf(backgroundCol.y, cloudColor.y, accumDensity);
+    out[2] = mixf(backgroundCol.z, cloudColor.z, accumDensity);
+    out[3] = fa * omaxf(1.0f - accumDensity, 0.0f);                               /* CC:496 */
+}
+
+/*
+ * Dispatch.  mode OM_FULL marches every pixel of the rows selected by (row_begin,row_stride,
+ * row_block): block index b = y / row_block is owned when (b - row_begin) % row_stride == 0 -- the
+ * union of the reference's 16 phase dispatches on a static camera.  mode OM_PHASE16 reproduces ONE
+ * reference dispatch (CC:291-301): only pixels (4*gx + o%4, 4*gy + o/4), o = int(sun.color.a).
+ * Pixels that are not written keep whatever `out` held (imageStore semantics).
+ * counters (optional): 4 uint32 per pixel {loop trips, 2D fetches, 3D fetches, lit steps}.
+ */
+int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_stride, int row_block,
+             float *out_rgba32f, uint32_t *counters, int nthreads) {
+    if (!s || !out_rgba32f || W <= 0 || H <= 0) return -1;
+    if (!s->placement.texels || !s->curl.texels || !s->lowres.texels || !s->hires.texels) return -3;
+    if (!__builtin_cpu_supports("fma")) return -4;
+    if (row_stride <= 0) row_stride = 1;
+    if (row_block <= 0) row_block = 1;
+    int off = (int)s->sun[11];                                                    /* CC:292 */
+    int ox = off % 4, oy = off / 4;
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#else
+    nthreads = 1;
+#endif
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+    for (int y = 0; y < H; y++) {
+        int blk = y / row_block;
+        if (blk < row_begin || ((blk - row_begin) % row_stride) != 0) continue;
+        if (mode == OM_PHASE16 && (y % 4) != oy) continue;
+        for (int x = 0; x < W; x++) {
+            if (mode == OM_PHASE16 && (x % 4) != ox) continue;
+            px_counters c = {0, 0, 0, 0};
+            float o[4];
+            march_pixel(s, x, y, W, H, o, &c);
+            size_t i = (size_t)y * W + x;
+            memcpy(out_rgba32f + 4 * i, o, 16);
+            if (counters) { counters[4 * i] = c.trips; counters[4 * i + 1] = c.n2d; counters[4 * i + 2] = c.n3d; counters[4 * i + 3] = c.lit; }
+        }
+    }
+    return 0;
+}
+
+/* expose the sampler for sampler-level tests */
+int om_sample(const om_scene *s, int slot, int filter, const float *uvw, int n, float *out_rgba) {
+    const ftex *t = slot == OM_TEX_PLACEMENT ? &s->placement : slot == OM_TEX_NIGHTSKY ? &s->nightsky :
+                    slot == OM_TEX_CURL ? &s->curl : slot == OM_TEX_LOWRES ? &s->lowres : &s->hires;
+    if (!t->texels) return -3;
+    for (int i = 0; i < n; i++) {
+        if (t->d > 1 || slot == OM_TEX_LOWRES || slot == OM_TEX_HIRES) sample3d(t, filter, uvw[3 * i], uvw[3 * i + 1], uvw[3 * i + 2], out_rgba + 4 * i);
+        else sample2d(t, filter, uvw[3 * i], uvw[3 * i + 1], out_rgba + 4 * i);
+    }
+    return 0;
+}
+
+/*
+ * HDR -> RGBA8 map used by the parity gate: tonemap.frag:11-28 (Uncharted-2, exposure 0.7,
+ * invGamma 1/2.2, white 50.2), vignette (:30-32) omitted; alpha = clamp(a,0,1).  round-half-up.
+ */
+static inline float uc2(float x) {
+    return (((x * ((0.15f * x) + (0.1f * 0.5f))) + (0.2f * 0.02f)) / ((x * ((0.15f * x) + 0.5f)) + (0.2f * 0.3f))) - (0.02f / 0.3f);
+}
+void om_tonemap_rgba8(const float *rgba32f, size_t npix, uint8_t *rgba8) {
+    float whitemap = 1.0f / uc2(50.2f);
+    for (size_t i = 0; i < npix; i++) {
+        for (int c = 0; c < 3; c++) {
+            float col = uc2(0.7f * rgba32f[4 * i + c]) * whitemap;
+            col = powf(col, 1.0f / 2.2f);
+            float q = clampf(col, 0.0f, 1.0f);           /* NaN (negative base) -> 0 */
+            rgba8[4 * i + c] = (uint8_t)floorf((255.0f * q) + 0.5f);
+        }
+        float a = clampf(rgba32f[4 * i + 3], 0.0f, 1.0f);
+        rgba8[4 * i + 3] = (uint8_t)floorf((255.0f * a) + 0.5f);
+    }
+}

@@ -1,0 +1,58 @@
+"""Build the sm_100a shared library (the C-ABI of include/marshmallow.h) in-tree with nvcc.
+
+    python project-marshmallow_b200/build.py [--force] [--ptxas-v]
+
+Output: project-marshmallow_b200/libmarshmallow_b200.so (git-ignored; travels to the GPU box with the
+snapshot).  -fmad=false is part of the arithmetic contract of the march's decision path.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libmarshmallow_b200.so")
+CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu"]
+CPP_SOURCES = ["host/sky_camera.cpp"]
+HEADERS = ["csrc/common.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h"]
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--cudart", "static"]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(HERE, s)) > t for s in CU_SOURCES + CPP_SOURCES + HEADERS + ["build.py"])
+
+
+def build_library(force=False, verbose=False, ptxas_v=False):
+    if not force and not _stale():
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in CU_SOURCES + CPP_SOURCES:
+        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        cmd = [NVCC] + ARCH + CFLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", os.path.join(HERE, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or ptxas_v or (verbose and out.strip()):
+            print(f"--- {src}\n{out}")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [NVCC] + ARCH + ["-shared", "--cudart", "static", "-o", LIB] + objs
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True, ptxas_v="--ptxas-v" in sys.argv))

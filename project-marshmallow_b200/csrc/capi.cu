@@ -1,0 +1,503 @@
+// capi.cu -- the C-ABI of include/marshmallow.h: context, texture residency, uniforms, dispatch.
+//
+// What the reference does with Vulkan objects in ComputeShader (Shader.h:286-377, Shader.cpp:633-992)
+// and Texture/Texture3D (Texture.cpp) is done here with CUDA objects:
+//   descriptor set 2 samplers  -> per-slot {uchar4 cudaArray + texture object, float4 linear copy}
+//   4 uniform buffers + memcpy -> MarchParams passed by value as a __grid_constant__ kernel argument
+//   descriptor set 0 image     -> pitch-linear float4 pointer (own, caller's or a peer GPU's) or a
+//                                 surface object over imported Vulkan memory
+//   vkCmdDispatch + submit     -> one kernel launch on the caller's stream
+// Memory plan per context: ~43 MB of read-only texture data (8+32 MB low-res, 1+4 MB placement,
+// <1 MB the rest), L2-resident on B200; output 16 B/pixel.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/marshmallow.h"
+#include "common.h"
+
+using namespace mm;
+
+struct TexSlot {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t obj = 0;
+    float4 *texels = nullptr;
+    int w = 0, h = 0, d = 0;
+    bool is3d = false;
+};
+
+struct mm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    TexSlot tex[TEX_COUNT];
+    float cam[40], sun[29], sky[13];
+    bool have_uniforms = false;
+    float *out = nullptr;          // bound output (may be external)
+    float *own_out = nullptr;      // allocation owned by the context
+    size_t pitch = 0;
+    int W = 0, H = 0;
+    cudaExternalMemory_t ext_mem = nullptr;
+    cudaMipmappedArray_t ext_mip = nullptr;
+    cudaSurfaceObject_t surf = 0;
+    uint32_t *counters = nullptr;
+    bool counters_on = false;
+    int filter = FILTER_EXACT;
+    float *scratch = nullptr;      // curl-noise scratch
+    uchar4 *stage = nullptr;       // upload staging (device)
+    size_t stage_bytes = 0;
+    char err[512];
+};
+
+static char g_create_err[512] = "";
+
+static int fail(mm_ctx *c, int code, const char *fmt, ...) {
+    char *dst = c ? c->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" {
+
+const char *mm_version(void) { return "marshmallow-b200 0.1 (sm_100a)"; }
+
+const char *mm_last_error(const mm_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int mm_create(int device, mm_ctx **out) {
+    mm_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, MM_ERR_ARG, "mm_create: out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, MM_ERR_CUDA, "mm_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, MM_ERR_ARG, "mm_create: device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, MM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, MM_ERR_CUDA, "mm_create: device %d is sm_%d%d; this build carries sm_100a code only", device, prop.major, prop.minor);
+    ctx = new (std::nothrow) mm_ctx();
+    if (!ctx) return fail(nullptr, MM_ERR_ARG, "out of host memory");
+    ctx->device = device;
+    ctx->err[0] = 0;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e != cudaSuccess) {
+        fail(nullptr, MM_ERR_CUDA, "mm_create: %s", cudaGetErrorString(e));
+        delete ctx;
+        return MM_ERR_CUDA;
+    }
+    *out = ctx;
+    return MM_OK;
+}
+
+static void free_slot(TexSlot &s) {
+    if (s.obj) cudaDestroyTextureObject(s.obj);
+    if (s.array) cudaFreeArray(s.array);
+    if (s.texels) cudaFree(s.texels);
+    s = TexSlot();
+}
+
+static void release_output(mm_ctx *ctx) {
+    if (ctx->surf) { cudaDestroySurfaceObject(ctx->surf); ctx->surf = 0; }
+    if (ctx->ext_mip) { cudaFreeMipmappedArray(ctx->ext_mip); ctx->ext_mip = nullptr; }
+    if (ctx->ext_mem) { cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr; }
+    if (ctx->own_out) { cudaFree(ctx->own_out); ctx->own_out = nullptr; }
+    if (ctx->counters) { cudaFree(ctx->counters); ctx->counters = nullptr; }
+    ctx->out = nullptr; ctx->pitch = 0; ctx->W = ctx->H = 0;
+}
+
+int mm_destroy(mm_ctx *ctx) {
+    if (!ctx) return MM_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < TEX_COUNT; i++) free_slot(ctx->tex[i]);
+    release_output(ctx);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->stage) cudaFree(ctx->stage);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return MM_OK;
+}
+
+// Make the texels in device buffer `src` (uchar4, [z][y][x]) resident in slot `slot`: a cudaArray with
+// the reference's sampler state for hardware filtering, and the float4 copy for exact filtering.
+static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, int d, bool is3d) {
+    TexSlot &s = ctx->tex[slot];
+    free_slot(s);
+    s.w = w; s.h = h; s.d = d; s.is3d = is3d;
+    size_t n = (size_t)w * h * d;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    if (is3d) {
+        CU(cudaMalloc3DArray(&s.array, &fmt, make_cudaExtent(w, h, d)));
+        cudaMemcpy3DParms cp = {};
+        cp.srcPtr = make_cudaPitchedPtr(const_cast<uchar4 *>(src), (size_t)w * 4, w, h);
+        cp.dstArray = s.array;
+        cp.extent = make_cudaExtent(w, h, d);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        CU(cudaMemcpy3DAsync(&cp, ctx->stream));
+    } else {
+        CU(cudaMallocArray(&s.array, &fmt, w, h));
+        CU(cudaMemcpy2DToArrayAsync(s.array, 0, 0, src, (size_t)w * 4, (size_t)w * 4, h, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = s.array;
+    cudaTextureDesc td = {};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeWrap;   // REPEAT (Texture.cpp:36-38, 322-324)
+    td.filterMode = cudaFilterModeLinear;                                              // LINEAR (Texture.cpp:33-34, 319-320)
+    td.readMode = cudaReadModeNormalizedFloat;                                         // RGBA8_UNORM (Texture.h:29,85)
+    td.normalizedCoords = 1;
+    CU(cudaCreateTextureObject(&s.obj, &rd, &td, nullptr));
+    CU(cudaMalloc(&s.texels, n * sizeof(float4)));
+    CU(launch_unorm_to_float(src, s.texels, n, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MM_OK;
+}
+
+static int ensure_stage(mm_ctx *ctx, size_t bytes) {
+    if (ctx->stage_bytes >= bytes) return MM_OK;
+    if (ctx->stage) { cudaFree(ctx->stage); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+    CU(cudaMalloc(&ctx->stage, bytes));
+    ctx->stage_bytes = bytes;
+    return MM_OK;
+}
+
+static int upload(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h, int d, bool is3d) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!rgba8 || w <= 0 || h <= 0 || d <= 0) return fail(ctx, MM_ERR_ARG, "upload: bad texture arguments");
+    if (slot < 0 || slot >= TEX_COUNT) return fail(ctx, MM_ERR_ARG, "upload: slot %d out of range", slot);
+    bool want3d = (slot == MM_TEX_LOWRES || slot == MM_TEX_HIRES);
+    if (want3d != is3d) return fail(ctx, MM_ERR_ARG, "upload: slot %d is a %s sampler", slot, want3d ? "3D" : "2D");
+    CU(cudaSetDevice(ctx->device));
+    size_t bytes = (size_t)w * h * d * 4;
+    int rc = ensure_stage(ctx, bytes);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(ctx->stage, rgba8, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return bind_texels(ctx, slot, ctx->stage, w, h, d, is3d);
+}
+
+int mm_upload_tex2d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h) { return upload(ctx, slot, rgba8, w, h, 1, false); }
+int mm_upload_tex3d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h, int d) { return upload(ctx, slot, rgba8, w, h, d, true); }
+
+// Gradient index of every lattice point the curl-noise Perlin can touch (coordinates -1..24, stored at
+// +1), following hashNoise / hashVec (ImageUtils.cpp:25-34) with the host C library's sinf -- see the
+// header of curl_noise.cu for why this one step stays on the host.
+static void build_curl_gradient_table(unsigned char *table) {
+    const float kx = 12.9898f, ky = 78.233f, kz = (float)47.387;
+    for (int z = -1; z < 25; z++)
+        for (int y = -1; y < 25; y++)
+            for (int x = -1; x < 25; x++) {
+                float d = (((float)x * kx) + ((float)y * ky)) + ((float)z * kz);
+                float n = sinf(d) * 43758.5453f;
+                n = n - floorf(n);
+                table[((z + 1) * 26 + (y + 1)) * 26 + (x + 1)] = (unsigned char)(int)floorf(12.f * n);
+            }
+}
+
+int mm_build_curl_noise(mm_ctx *ctx, uint8_t *out_host) {
+    if (!ctx) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = 128 * 128, TBL = 26 * 26 * 26;
+    if (!ctx->scratch) CU(cudaMalloc(&ctx->scratch, (15 * N + 8) * sizeof(float) + TBL));
+    unsigned char *dtable = reinterpret_cast<unsigned char *>(ctx->scratch + 15 * N + 8);
+    static unsigned char htable[26 * 26 * 26];
+    build_curl_gradient_table(htable);
+    CU(cudaMemcpyAsync(dtable, htable, TBL, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ensure_stage(ctx, N * 4);
+    if (rc) return rc;
+    CU(launch_curl_noise(ctx->stage, ctx->scratch, dtable, ctx->stream));
+    if (out_host) CU(cudaMemcpyAsync(out_host, ctx->stage, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return bind_texels(ctx, MM_TEX_CURL, ctx->stage, 128, 128, 1, false);
+}
+
+int mm_build_noise_volumes(mm_ctx *ctx, uint64_t seed64, uint8_t *out_low, uint8_t *out_hi) {
+    if (!ctx) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const size_t NL = (size_t)128 * 128 * 128, NH = (size_t)32 * 32 * 32;
+    int rc = ensure_stage(ctx, (NL + NH) * 4);
+    if (rc) return rc;
+    uint32_t seed = (uint32_t)(seed64 ^ (seed64 >> 32));
+    uchar4 *low = ctx->stage, *hi = ctx->stage + NL;
+    CU(launch_noise_volumes(seed, low, hi, ctx->stream));
+    if (out_low) CU(cudaMemcpyAsync(out_low, low, NL * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_hi) CU(cudaMemcpyAsync(out_hi, hi, NH * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    rc = bind_texels(ctx, MM_TEX_LOWRES, low, 128, 128, 128, true);
+    if (rc) return rc;
+    return bind_texels(ctx, MM_TEX_HIRES, hi, 32, 32, 32, true);
+}
+
+int mm_set_uniforms(mm_ctx *ctx, const void *camera160, const void *camera_prev160, const void *sun116, const void *sky52) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!camera160 || !sun116 || !sky52) return fail(ctx, MM_ERR_ARG, "mm_set_uniforms: null uniform block");
+    (void)camera_prev160;   // UniformCameraObjectPrev is declared but never read by the march (CC:19-23)
+    memcpy(ctx->cam, camera160, 160);
+    memcpy(ctx->sun, sun116, 116);
+    memcpy(ctx->sky, sky52, 52);
+    ctx->have_uniforms = true;
+    return MM_OK;
+}
+
+static int size_counters(mm_ctx *ctx) {
+    if (ctx->counters) { cudaFree(ctx->counters); ctx->counters = nullptr; }
+    if (ctx->counters_on && ctx->W > 0) {
+        CU(cudaMalloc(&ctx->counters, (size_t)ctx->W * ctx->H * 16));
+        CU(cudaMemset(ctx->counters, 0, (size_t)ctx->W * ctx->H * 16));
+    }
+    return MM_OK;
+}
+
+int mm_bind_output_linear(mm_ctx *ctx, float *dptr, size_t pitch, int w, int h) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!dptr || w <= 0 || h <= 0 || pitch < (size_t)w * 16 || (pitch & 15) || ((uintptr_t)dptr & 15))
+        return fail(ctx, MM_ERR_ARG, "mm_bind_output_linear: need a 16-byte aligned pointer and pitch >= 16*w");
+    CU(cudaSetDevice(ctx->device));
+    release_output(ctx);
+    ctx->out = dptr; ctx->pitch = pitch; ctx->W = w; ctx->H = h;
+    return size_counters(ctx);
+}
+
+int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *pitch_out) {
+    if (!ctx) return MM_ERR_ARG;
+    if (w <= 0 || h <= 0) return fail(ctx, MM_ERR_ARG, "mm_alloc_output: bad size");
+    CU(cudaSetDevice(ctx->device));
+    release_output(ctx);
+    CU(cudaMalloc(&ctx->own_out, (size_t)w * h * 16));
+    ctx->out = ctx->own_out; ctx->pitch = (size_t)w * 16; ctx->W = w; ctx->H = h;
+    if (dptr_out) *dptr_out = ctx->out;
+    if (pitch_out) *pitch_out = ctx->pitch;
+    return size_counters(ctx);
+}
+
+// Vulkan interop: the engine exports the VkDeviceMemory behind backgroundTexture
+// (VK_FORMAT_R32G32B32A32_SFLOAT, optimal tiling, STORAGE|SAMPLED; VulkanApplication.cpp:247-250) as an
+// opaque fd; it is imported here as a one-level mipmapped array and written through a surface object.
+int mm_bind_output_external_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, int w, int h) {
+    if (!ctx) return MM_ERR_ARG;
+    if (fd < 0 || alloc_bytes < (size_t)w * h * 16 || w <= 0 || h <= 0) return fail(ctx, MM_ERR_ARG, "mm_bind_output_external_fd: bad arguments");
+    CU(cudaSetDevice(ctx->device));
+    release_output(ctx);
+    cudaExternalMemoryHandleDesc hd = {};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = alloc_bytes;
+    CU(cudaImportExternalMemory(&ctx->ext_mem, &hd));
+    cudaExternalMemoryMipmappedArrayDesc md = {};
+    md.offset = 0;
+    md.formatDesc = cudaCreateChannelDesc<float4>();
+    md.extent = make_cudaExtent(w, h, 0);
+    md.flags = cudaArraySurfaceLoadStore;
+    md.numLevels = 1;
+    CU(cudaExternalMemoryGetMappedMipmappedArray(&ctx->ext_mip, ctx->ext_mem, &md));
+    cudaArray_t level0;
+    CU(cudaGetMipmappedArrayLevel(&level0, ctx->ext_mip, 0));
+    cudaResourceDesc rd = {};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = level0;
+    CU(cudaCreateSurfaceObject(&ctx->surf, &rd));
+    ctx->W = w; ctx->H = h;
+    return size_counters(ctx);
+}
+
+int mm_set_filter_mode(mm_ctx *ctx, int filter) {
+    if (!ctx) return MM_ERR_ARG;
+    if (filter < MM_FILTER_EXACT || filter > MM_FILTER_HYBRID) return fail(ctx, MM_ERR_ARG, "mm_set_filter_mode: unknown mode %d", filter);
+    ctx->filter = filter;
+    return MM_OK;
+}
+
+int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream_v) {
+    if (!ctx) return MM_ERR_ARG;
+    if (mode != MM_FULL && mode != MM_PHASE16) return fail(ctx, MM_ERR_ARG, "mm_dispatch: unknown mode %d", mode);
+    if (row_begin < 0 || row_stride <= 0 || row_block <= 0) return fail(ctx, MM_ERR_ARG, "mm_dispatch: bad row partition (%d,%d,%d)", row_begin, row_stride, row_block);
+    if (!ctx->have_uniforms) return fail(ctx, MM_ERR_STATE, "mm_dispatch: uniforms were never set");
+    if (!ctx->out && !ctx->surf) return fail(ctx, MM_ERR_STATE, "mm_dispatch: no output image bound");
+    static const int need[4] = {MM_TEX_PLACEMENT, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES};
+    for (int i = 0; i < 4; i++)
+        if (!ctx->tex[need[i]].texels) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+
+    MarchParams p;
+    memcpy(p.cam, ctx->cam, sizeof p.cam);
+    memcpy(p.sun, ctx->sun, sizeof p.sun);
+    memcpy(p.sky, ctx->sky, sizeof p.sky);
+    for (int i = 0; i < TEX_COUNT; i++) {
+        const TexSlot &s = ctx->tex[i];
+        p.tex[i].texels = s.texels; p.tex[i].obj = s.obj;
+        p.tex[i].w = s.w; p.tex[i].h = s.h; p.tex[i].d = s.d;
+        p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
+    }
+    p.out = ctx->out; p.pitch = ctx->pitch; p.surf = ctx->surf;
+    p.counters = ctx->counters_on ? ctx->counters : nullptr;
+    p.W = ctx->W; p.H = ctx->H; p.mode = mode;
+    p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block;
+    if (mode == MM_FULL) {
+        int nblocks = (ctx->H + row_block - 1) / row_block;
+        int owned = row_begin < nblocks ? (nblocks - row_begin + row_stride - 1) / row_stride : 0;
+        p.owned_rows = owned * row_block;
+        p.grid_w = ctx->W;
+    } else {
+        p.owned_rows = (ctx->H + 3) / 4;
+        p.grid_w = (ctx->W + 3) / 4;
+    }
+    CU(cudaEventRecord(ctx->ev0, stream));
+    CU(launch_cloud_march(p, ctx->filter, stream));
+    CU(cudaEventRecord(ctx->ev1, stream));
+    ctx->timed = true;
+    return MM_OK;
+}
+
+int mm_synchronize(mm_ctx *ctx) {
+    if (!ctx) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaDeviceSynchronize());
+    return MM_OK;
+}
+
+int mm_last_kernel_ms(mm_ctx *ctx, float *ms) {
+    if (!ctx || !ms) return MM_ERR_ARG;
+    if (!ctx->timed) return fail(ctx, MM_ERR_STATE, "mm_last_kernel_ms: nothing dispatched yet");
+    CU(cudaEventSynchronize(ctx->ev1));
+    CU(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return MM_OK;
+}
+
+int mm_read_output(mm_ctx *ctx, float *host_out) {
+    if (!ctx || !host_out) return MM_ERR_ARG;
+    if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_read_output: no linear output bound");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy2D(host_out, (size_t)ctx->W * 16, ctx->out, ctx->pitch, (size_t)ctx->W * 16, ctx->H, cudaMemcpyDeviceToHost));
+    return MM_OK;
+}
+
+int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, const void *sky52, int mode, float *out_host) {
+    if (!ctx || !out_host) return MM_ERR_ARG;
+    int rc = mm_set_uniforms(ctx, camera160, nullptr, sun116, sky52);
+    if (rc) return rc;
+    if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_render_to_host: no linear output bound (mm_alloc_output)");
+    rc = mm_dispatch(ctx, mode, 0, 1, 1, nullptr);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(out_host, (size_t)ctx->W * 16, ctx->out, ctx->pitch, (size_t)ctx->W * 16, ctx->H, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MM_OK;
+}
+
+int mm_tonemap_rgba8(mm_ctx *ctx, uint8_t *dst, int dst_is_device, void *stream_v) {
+    if (!ctx || !dst) return MM_ERR_ARG;
+    if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_tonemap_rgba8: no linear output bound");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    size_t bytes = (size_t)ctx->W * ctx->H * 4;
+    if (dst_is_device) {
+        CU(launch_tonemap(ctx->out, ctx->pitch, ctx->W, ctx->H, reinterpret_cast<uchar4 *>(dst), stream));
+        return MM_OK;
+    }
+    uchar4 *tmp = nullptr;
+    CU(cudaMalloc(&tmp, bytes));
+    cudaError_t e = launch_tonemap(ctx->out, ctx->pitch, ctx->W, ctx->H, tmp, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp, bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_tonemap_rgba8: %s", cudaGetErrorString(e));
+    return MM_OK;
+}
+
+int mm_enable_counters(mm_ctx *ctx, int enable) {
+    if (!ctx) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    ctx->counters_on = enable != 0;
+    return size_counters(ctx);
+}
+
+int mm_read_counters(mm_ctx *ctx, uint32_t *host_out) {
+    if (!ctx || !host_out) return MM_ERR_ARG;
+    if (!ctx->counters) return fail(ctx, MM_ERR_STATE, "mm_read_counters: counters are not enabled");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(host_out, ctx->counters, (size_t)ctx->W * ctx->H * 16, cudaMemcpyDeviceToHost));
+    return MM_OK;
+}
+
+int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, float *out_host) {
+    if (!ctx || !uvw_host || !out_host || n < 0) return MM_ERR_ARG;
+    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].texels) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
+    if (filter != MM_FILTER_EXACT && filter != MM_FILTER_HW) return fail(ctx, MM_ERR_ARG, "mm_sample: filter must be EXACT or HW");
+    CU(cudaSetDevice(ctx->device));
+    float *duvw = nullptr; float4 *dout = nullptr;
+    CU(cudaMalloc(&duvw, (size_t)n * 12 + 16));
+    cudaError_t e = cudaMalloc(&dout, (size_t)n * 16 + 16);
+    const TexSlot &s = ctx->tex[slot];
+    TexDev t = {s.texels, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(duvw, uvw_host, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_sample_probe(t, s.is3d, filter, duvw, n, dout, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(duvw); cudaFree(dout);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_sample: %s", cudaGetErrorString(e));
+    return MM_OK;
+}
+
+int mm_ipc_get_handle(mm_ctx *ctx, void *dptr, uint8_t handle_out[64]) {
+    if (!ctx || !dptr || !handle_out) return MM_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle_out, &h, 64);
+    return MM_OK;
+}
+
+int mm_ipc_open_handle(mm_ctx *ctx, const uint8_t handle[64], void **dptr_out) {
+    if (!ctx || !handle || !dptr_out) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(dptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return MM_OK;
+}
+
+int mm_ipc_close_handle(mm_ctx *ctx, void *dptr) {
+    if (!ctx || !dptr) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaIpcCloseMemHandle(dptr));
+    return MM_OK;
+}
+
+int mm_det_pow(mm_ctx *ctx, const float *x, const float *y, int n, float *out) {
+    if (!ctx || !x || !y || !out || n < 0) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    float *d = nullptr;
+    CU(cudaMalloc(&d, (size_t)n * 12 + 16));
+    cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_det_pow(d, d + n, n, d + 2 * (size_t)n, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_det_pow: %s", cudaGetErrorString(e));
+    return MM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// common.h -- device-side parameter blocks and kernel launchers shared by the C-ABI (capi.cu)
+// and the kernels.  Internal; the public boundary is include/marshmallow.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mm {
+
+// One bound texture.  `texels` is the EXACT-mode copy: one float4 per texel holding byte/255.0f
+// (IEEE divide, done once at upload), x fastest.  `obj` is the hardware-filtered view of the same
+// bytes: uchar4 cudaArray, normalised coordinates, wrap addressing, linear filter, UNORM -> float
+// (the reference sampler: Texture.cpp:29-52, 315-338).
+struct TexDev {
+    const float4 *texels;
+    cudaTextureObject_t obj;
+    int w, h, d;
+    int pow2;   // all extents are powers of two -> wrap by mask
+};
+
+enum { TEX_PLACEMENT = 0, TEX_NIGHTSKY = 1, TEX_CURL = 2, TEX_LOWRES = 3, TEX_HIRES = 4, TEX_COUNT = 5 };
+enum { FILTER_EXACT = 0, FILTER_HW = 1, FILTER_HYBRID = 2 };
+enum { DISPATCH_FULL = 0, DISPATCH_PHASE16 = 1 };
+
+struct MarchParams {
+    float cam[40];   // UniformCameraObject (Shader.h:24-29)
+    float sun[29];   // UniformSunObject    (SkyManager.h:8-14)
+    float sky[13];   // UniformSkyObject    (SkyManager.h:28-36)
+    TexDev tex[TEX_COUNT];
+    float *out;                  // pitch-linear float4 image (may be peer memory), or nullptr when surf is used
+    size_t pitch;                // bytes
+    cudaSurfaceObject_t surf;    // external (Vulkan) image, when out == nullptr
+    uint32_t *counters;          // 4 x uint32 per pixel or nullptr
+    int W, H;
+    int mode;                    // DISPATCH_*
+    int row_begin, row_stride, row_block;
+    int owned_rows;              // rows this dispatch enumerates (FULL), virtual rows (PHASE16)
+    int grid_w;                  // pixel columns enumerated (W, or ceil(W/4) in PHASE16)
+};
+
+cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);
+cudaError_t launch_sample_probe(const TexDev &t, int is3d, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
+cudaError_t launch_det_pow(const float *x, const float *y, int n, float *out, cudaStream_t stream);
+cudaError_t launch_unorm_to_float(const uchar4 *src, float4 *dst, size_t n, cudaStream_t stream);
+cudaError_t launch_tonemap(const float *src, size_t pitch, int W, int H, uchar4 *dst, cudaStream_t stream);
+cudaError_t launch_curl_noise(uchar4 *dst128x128, float *scratch /* 15*128*128 + 8 floats */, const unsigned char *gradient_table /* 26^3, device */, cudaStream_t stream);
+cudaError_t launch_noise_volumes(uint32_t seed, uchar4 *low128, uchar4 *hi32, cudaStream_t stream);
+
+}  // namespace mm

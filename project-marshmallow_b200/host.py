@@ -1,0 +1,196 @@
+"""Python mirror of the reference's ComputeShader interface (Shader.h:286-377) over the C-ABI.
+
+    reference (C++/Vulkan)                                   here
+    ComputeShader(device, ..., out, outPrev, placement,      ComputeShader(device, extent, placement,
+                  nightSky, curl, lowRes, hiRes)                           nightSky, curl, lowRes, hiRes)
+    updateUniformBuffers(cam, camPrev, sky, sun)             updateUniformBuffers(cam, camPrev, sky, sun)
+    bindShader(cmdBuf); vkCmdDispatch; vkQueueSubmit         dispatch(mode, stream=...)
+    backgroundTexture (VkImage rgba32f)                      output pointer / readOutput()
+
+Errors raise MarshmallowError (the reference throws std::runtime_error).  No torch types cross the
+boundary: device pointers and streams are passed as integers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import MarshmallowError, _ptr
+
+
+class SkyManager:
+    """Value producer mirroring SkyManager (SkyManager.h:51-77): rebuildSkyFromNewSun / setTime / getSun / getSky."""
+
+    def __init__(self, turbidity=10.0):
+        self.elevation, self.azimuth = float(np.float32(np.pi) / 4), float(np.float32(np.pi) / 8)
+        self.wind = (1.0, 0.05, 1.0)
+        self.time = 0.0
+        self.turbidity = turbidity
+        self.pixel_phase = 0
+
+    def rebuildSkyFromNewSun(self, elevation, azimuth):
+        self.elevation, self.azimuth = elevation, azimuth
+
+    def setWindDirection(self, d):
+        self.wind = tuple(d)
+
+    def setTime(self, t):
+        self.time = t
+
+    def _build(self):
+        return capi.host_sky(self.elevation, self.azimuth, self.wind, self.time, self.pixel_phase, self.turbidity)
+
+    def getSun(self):
+        return self._build()[0]
+
+    def getSky(self):
+        return self._build()[1]
+
+
+class Camera:
+    """Value producer mirroring Camera (camera.h): position + yaw/pitch -> UniformCameraObject bytes."""
+
+    def __init__(self, position, yaw, pitch, fov=45.0, aspect=1920.0 / 1080.0):
+        self.position, self.yaw, self.pitch, self.fov, self.aspect = tuple(position), yaw, pitch, fov, aspect
+
+    def getUniform(self):
+        return capi.host_camera(self.position, self.yaw, self.pitch, self.fov, self.aspect)
+
+
+class ComputeShader:
+    def __init__(self, device, extent, placement=None, nightSky=None, curl=None, lowRes=None, hiRes=None):
+        self._lib = capi.load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.mm_create(int(device), C.byref(self._ctx))
+        if rc:
+            raise MarshmallowError(rc, self._lib.mm_last_error(None).decode())
+        self.width, self.height = int(extent[0]), int(extent[1])
+        self.out_ptr, self.out_pitch = None, None
+        for slot, tex in ((capi.MM_TEX_PLACEMENT, placement), (capi.MM_TEX_NIGHTSKY, nightSky), (capi.MM_TEX_CURL, curl),
+                          (capi.MM_TEX_LOWRES, lowRes), (capi.MM_TEX_HIRES, hiRes)):
+            if tex is not None:
+                self.uploadTexture(slot, tex)
+
+    # ---- plumbing
+    def _check(self, rc):
+        if rc:
+            raise MarshmallowError(rc, self._lib.mm_last_error(self._ctx).decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.mm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- textures (Texture::initFromFile / Texture3D::initFromFile)
+    def uploadTexture(self, slot, rgba8):
+        a = np.ascontiguousarray(rgba8, np.uint8)
+        if a.ndim == 3:
+            h, w, _ = a.shape
+            self._check(self._lib.mm_upload_tex2d(self._ctx, slot, _ptr(a), w, h))
+        else:
+            d, h, w, _ = a.shape
+            self._check(self._lib.mm_upload_tex3d(self._ctx, slot, _ptr(a), w, h, d))
+
+    def buildCurlNoise(self, want_copy=True):
+        out = np.zeros((128, 128, 4), np.uint8) if want_copy else None
+        self._check(self._lib.mm_build_curl_noise(self._ctx, _ptr(out) if want_copy else None))
+        return out
+
+    def buildNoiseVolumes(self, seed=0, want_copy=True):
+        low = np.zeros((128, 128, 128, 4), np.uint8) if want_copy else None
+        hi = np.zeros((32, 32, 32, 4), np.uint8) if want_copy else None
+        self._check(self._lib.mm_build_noise_volumes(self._ctx, seed, _ptr(low) if want_copy else None, _ptr(hi) if want_copy else None))
+        return low, hi
+
+    # ---- output image (descriptor set 0)
+    def allocOutput(self):
+        p, pitch = C.c_void_p(), C.c_size_t()
+        self._check(self._lib.mm_alloc_output(self._ctx, self.width, self.height, C.byref(p), C.byref(pitch)))
+        self.out_ptr, self.out_pitch = p.value, pitch.value
+        return self.out_ptr, self.out_pitch
+
+    def bindOutput(self, device_ptr, pitch_bytes=None):
+        pitch = pitch_bytes or self.width * 16
+        self._check(self._lib.mm_bind_output_linear(self._ctx, C.c_void_p(int(device_ptr)), pitch, self.width, self.height))
+        self.out_ptr, self.out_pitch = int(device_ptr), pitch
+
+    # ---- multi-GPU: CUDA-IPC export / import of the output image
+    def ipcGetHandle(self, device_ptr):
+        h = np.zeros(64, np.uint8)
+        self._check(self._lib.mm_ipc_get_handle(self._ctx, C.c_void_p(int(device_ptr)), _ptr(h)))
+        return h.tobytes()
+
+    def ipcOpenHandle(self, handle):
+        h = np.frombuffer(handle, np.uint8).copy()
+        p = C.c_void_p()
+        self._check(self._lib.mm_ipc_open_handle(self._ctx, _ptr(h), C.byref(p)))
+        return p.value
+
+    def ipcCloseHandle(self, device_ptr):
+        self._check(self._lib.mm_ipc_close_handle(self._ctx, C.c_void_p(int(device_ptr))))
+
+    # ---- per frame
+    def updateUniformBuffers(self, cam, camPrev, sky, sun):
+        cam, sky, sun = (np.ascontiguousarray(x, np.float32) for x in (cam, sky, sun))
+        assert cam.nbytes == 160 and sun.nbytes == 116 and sky.nbytes == 52
+        prev = _ptr(np.ascontiguousarray(camPrev, np.float32)) if camPrev is not None else None
+        self._check(self._lib.mm_set_uniforms(self._ctx, _ptr(cam), prev, _ptr(sun), _ptr(sky)))
+
+    def setFilterMode(self, mode):
+        self._check(self._lib.mm_set_filter_mode(self._ctx, mode))
+
+    def dispatch(self, mode=capi.MM_FULL, row_begin=0, row_stride=1, row_block=1, stream=None):
+        self._check(self._lib.mm_dispatch(self._ctx, mode, row_begin, row_stride, row_block, C.c_void_p(stream) if stream else None))
+
+    def synchronize(self):
+        self._check(self._lib.mm_synchronize(self._ctx))
+
+    def lastKernelMs(self):
+        ms = C.c_float()
+        self._check(self._lib.mm_last_kernel_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def renderToHost(self, cam, sky, sun, mode=capi.MM_FULL, out=None):
+        """End-to-end call: host uniforms in, host image out."""
+        cam, sky, sun = (np.ascontiguousarray(x, np.float32) for x in (cam, sky, sun))
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self._lib.mm_render_to_host(self._ctx, _ptr(cam), _ptr(sun), _ptr(sky), mode, _ptr(out)))
+        return out
+
+    def readOutput(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self._lib.mm_read_output(self._ctx, _ptr(out)))
+        return out
+
+    def tonemapRGBA8(self):
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        self._check(self._lib.mm_tonemap_rgba8(self._ctx, _ptr(out), 0, None))
+        return out
+
+    # ---- diagnostics
+    def enableCounters(self, on=True):
+        self._check(self._lib.mm_enable_counters(self._ctx, int(on)))
+
+    def readCounters(self):
+        out = np.empty((self.height, self.width, 4), np.uint32)
+        self._check(self._lib.mm_read_counters(self._ctx, _ptr(out)))
+        return out
+
+    def sample(self, slot, filter_mode, uvw):
+        uvw = np.ascontiguousarray(uvw, np.float32).reshape(-1, 3)
+        out = np.empty((uvw.shape[0], 4), np.float32)
+        self._check(self._lib.mm_sample(self._ctx, slot, filter_mode, _ptr(uvw), uvw.shape[0], _ptr(out)))
+        return out
+
+    def detPow(self, x, y):
+        x, y = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32)
+        out = np.empty_like(x)
+        self._check(self._lib.mm_det_pow(self._ctx, _ptr(x), _ptr(y), x.size, _ptr(out)))
+        return out

@@ -1,0 +1,58 @@
+"""Multi-GPU sharding of one frame: row-cyclic partition + peer-mapped output image.
+
+New work (the reference is single-device).  Pixels are independent given the replicated read-only
+textures (~43 MB per GPU) and 328 bytes of uniforms, so the frame shards with NO data-path collective:
+rank r marches row blocks b with b % world == r (blocks of `row_block` rows; contiguous bands would be
+badly unbalanced because rows below the horizon are free) and its kernel stores finished
+pixels straight into rank 0's image, mapped through CUDA IPC over NVLink.  torch.distributed is only the
+plumbing that carries the 64-byte handle and the barriers.
+"""
+import numpy as np
+
+
+def owned_rows(H, rank, world, row_block):
+    """Rows marched by `rank` -- the same enumeration as the kernel (csrc/cloud_march.cu) and mm_dispatch."""
+    rows = []
+    nblocks = (H + row_block - 1) // row_block
+    for b in range(rank, nblocks, world):
+        rows.extend(y for y in range(b * row_block, min(H, (b + 1) * row_block)))
+    return np.asarray(rows, dtype=np.int64)
+
+
+def partition_is_exact_cover(H, world, row_block):
+    seen = np.zeros(H, np.int32)
+    for r in range(world):
+        seen[owned_rows(H, r, world, row_block)] += 1
+    return bool((seen == 1).all())
+
+
+def exchange_handle(handle, rank, world, dist=None, src=0):
+    """Broadcast rank `src`'s 64-byte IPC handle to every rank (works on gloo and nccl process groups)."""
+    if world == 1:
+        return handle
+    box = [handle if rank == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+class SharedFrame:
+    """The output image of a sharded frame: allocated on rank 0, mapped on every other rank."""
+
+    def __init__(self, cs, rank, world, dist=None):
+        self.cs, self.rank, self.world = cs, rank, world
+        self.remote_ptr = None
+        handle = None
+        if rank == 0:
+            self.ptr, self.pitch = cs.allocOutput()
+            if world > 1:
+                handle = cs.ipcGetHandle(self.ptr)
+        handle = exchange_handle(handle, rank, world, dist)
+        if rank != 0:
+            self.remote_ptr = cs.ipcOpenHandle(handle)
+            self.ptr, self.pitch = self.remote_ptr, cs.width * 16
+            cs.bindOutput(self.ptr, self.pitch)
+
+    def close(self):
+        if self.remote_ptr is not None:
+            self.cs.ipcCloseHandle(self.remote_ptr)
+            self.remote_ptr = None

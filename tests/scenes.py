@@ -1,0 +1,62 @@
+"""The frozen synthetic inputs of SURVEY.md section 8(d): configs C1..C5 (test/bench infrastructure).
+
+No RNG is involved in the march: a frame is a pure function of the three uniform blocks and the four
+textures.  Uniform values come from the library's host-side SkyManager/Camera mirrors
+(mm_host_sky / mm_host_camera, CPU only).
+"""
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSETS = os.path.join(ROOT, "tests", "golden", "assets")
+DEG2RAD = 0.01745  # camera.h:15
+
+
+def load_assets():
+    out = {}
+    for key, name in (("placement", "CloudPlacement"), ("curl", "CurlNoiseFBM"), ("lowres", "lowResCloudShape"), ("hires", "hiResCloudShape")):
+        out[key] = np.load(os.path.join(ASSETS, name + ".npz"))["rgba8"]
+    out["manifest"] = json.load(open(os.path.join(ASSETS, "MANIFEST.json")))
+    return out
+
+
+def constant_placement(r, b, size=64):
+    """BASELINE's 'coverage' knob realised as a placement texture (SURVEY finding 3): R = coverage, B = cloud type."""
+    t = np.zeros((size, size, 4), np.uint8)
+    t[..., 0], t[..., 2], t[..., 3] = r, b, 255
+    return t
+
+
+CONFIGS = {
+    # name: (W, H, camera pos, yaw, pitch(rad, negative looks up), elevation, azimuth, wind xyz, time, placement)
+    "C1": dict(W=320, H=180, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,
+               wind=(1.0, 0.05, 1.0), time=0.0, placement="shipped"),
+    "C2": dict(W=1920, H=1080, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,
+               wind=(1.0, 0.05, 1.0), time=0.0, placement="shipped"),
+    "C2b": dict(W=1920, H=1080, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,
+                wind=(1.0, 0.05, 1.0), time=0.0, placement=(128, 255)),
+    "C3": dict(W=3840, H=2160, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-10 * DEG2RAD, elevation=0.008, azimuth=0.25,
+               wind=(1.0, 0.05, 1.0), time=0.0, placement="shipped"),
+    "C5": dict(W=7680, H=4320, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,
+               wind=(1.0, 0.05, 1.0), time=0.0, placement=(230, 255)),
+    "C5b": dict(W=7680, H=4320, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,
+                wind=(1.0, 0.05, 1.0), time=0.0, placement=(128, 128)),
+}
+
+
+def make_scene(mm, name, assets, W=None, H=None, time=None, pixel_phase=0, **over):
+    """-> dict(W, H, cam, sun, sky, textures{placement,curl,lowres,hires}).  W/H override keeps the same view
+    (aspect stays 16:9 as in camera.h:31), so any config can be rendered at a resolution the oracle finishes quickly."""
+    cfg = dict(CONFIGS[name])
+    cfg.update(over)
+    if W:
+        cfg["W"], cfg["H"] = W, H
+    if time is not None:
+        cfg["time"] = time
+    cam = mm.host_camera(cfg["pos"], cfg["yaw"], cfg["pitch"], 45.0, 1920.0 / 1080.0)
+    sun, sky = mm.host_sky(cfg["elevation"], cfg["azimuth"], cfg["wind"], cfg["time"], pixel_phase)
+    tex = {k: assets[k] for k in ("curl", "lowres", "hires")}
+    tex["placement"] = assets["placement"] if cfg["placement"] == "shipped" else constant_placement(*cfg["placement"])
+    return dict(name=name, W=cfg["W"], H=cfg["H"], cam=cam, sun=sun, sky=sky, textures=tex)
