@@ -124,6 +124,11 @@ MM_API int mm_sample(mm_ctx *ctx, int slot, int filter_mode, const float *uvw_ho
 /* the deterministic pow of the decision path, evaluated on the GPU (bit-exactness probe) */
 MM_API int mm_det_pow(mm_ctx *ctx, const float *x_host, const float *y_host, int n, float *out_host);
 
+/* exhaustive self-test of the exact divide-by-constant sequence the march uses (csrc/cloud_march.cu,
+ * div_const): for constant number `which` (0 .. count-1; MM_ERR_ARG beyond) compares it with the IEEE
+ * divide over every binary32 dividend and returns the number of mismatching bit patterns (must be 0). */
+MM_API int mm_selftest_div(mm_ctx *ctx, int which, float *constant_out, unsigned long long *mismatches_out);
+
 /* ---- multi-GPU plumbing (new work: the reference is single-device, VulkanApplication.cpp:639-687).
  * One process per GPU.  Rank 0 exports the allocation behind its output image as a 64-byte CUDA-IPC
  * handle; the other ranks open it and bind the mapped pointer with mm_bind_output_linear, so their

@@ -22,9 +22,13 @@
  *     max(x,y) = (x<y)?y:x;  min(x,y) = (y<x)?y:x;  clamp(x,lo,hi): r = (x>lo)?x:lo; (r<hi)?r:hi
  *     (NaN -> lo, Q6);
  *     smoothstep(e0,e1,x): t = clamp((x-e0)/(e1-e0),0,1); t*t*(3-2*t);
- *   - the texture unit is restated as: texel = byte/255.0f (IEEE divide), unnormalised coordinate
- *     U = u*N - 0.5f, i0 = floor(U), weight a = U - i0, REPEAT wrap, and three (two) nested
- *     lerps  lerp(p,q,a) = fmaf(a, q-p, p)  in x, then y, then z  (filter mode OM_FILTER_FP32).
+ *   - the texture unit is restated as: unnormalised coordinate U = u*N - 0.5f, i0 = floor(U),
+ *     weight a = U - i0, REPEAT wrap; the UNORM8 texels enter as their integer values 0..255
+ *     (exact in binary32), are combined by three (two) nested fused lerps
+ *     lerp(p,q,a) = fmaf(a, q-p, p)  in x, then y, then z, and the result is scaled once by the
+ *     binary32 constant 1.0f/255.0f  (filter mode OM_FILTER_FP32).  Vulkan leaves the precision of
+ *     UNORM conversion and filtering to the implementation; this order (filter, then normalise)
+ *     is the one a GPU can follow at one multiply per channel and keeps 0 -> 0.0 and 255 -> 1.0;
  *     OM_FILTER_FIX8 rounds each weight to 8 fractional bits first (what NVIDIA texture units do,
  *     CUDA C Programming Guide "Linear Filtering"); it exists to measure how sensitive the march
  *     is to sampler precision, not as a second truth;
@@ -129,7 +133,7 @@ float om_det_powf(float x, float y) {
 /* ------------------------------------------------------------------------------------------ */
 /* software sampler: Texture.cpp:29-52 (2D) and :315-338 (3D): LINEAR, REPEAT, LOD 0, RGBA8_UNORM */
 typedef struct {
-    const float *texels;  /* w*h*d*4 floats, byte/255.0f */
+    const float *texels;  /* w*h*d*4 floats holding the byte values 0..255 */
     int w, h, d;
 } ftex;
 
@@ -163,7 +167,7 @@ static void sample2d(const ftex *t, int filter, float u, float v, float out[4]) 
     for (int c = 0; c < 4; c++) {
         float top = lerpf(t00[c], t10[c], a);
         float bot = lerpf(t01[c], t11[c], a);
-        out[c] = lerpf(top, bot, b);
+        out[c] = lerpf(top, bot, b) * (1.0f / 255.0f);
     }
 }
 
@@ -185,7 +189,7 @@ static void sample3d(const ftex *t, int filter, float u, float v, float w, float
         float x11 = lerpf(t011[c], t111[c], a);
         float y0v = lerpf(x00, x10, b);
         float y1v = lerpf(x01, x11, b);
-        out[c] = lerpf(y0v, y1v, g);
+        out[c] = lerpf(y0v, y1v, g) * (1.0f / 255.0f);
     }
 }
 
@@ -223,7 +227,7 @@ int om_scene_set_texture(om_scene *s, int slot, const uint8_t *rgba8, int w, int
     size_t n = (size_t)w * h * d * 4;
     float *f = (float *)malloc(n * sizeof(float));
     if (!f) return -2;
-    for (size_t i = 0; i < n; i++) f[i] = (float)rgba8[i] / 255.0f;   /* UNORM8 -> float */
+    for (size_t i = 0; i < n; i++) f[i] = (float)rgba8[i];             /* integer texel values; normalised after filtering */
     free(s->store[slot]);
     s->store[slot] = f;
     ftex t = {f, w, h, d};

@@ -72,6 +72,7 @@ def load_library():
         "mm_last_kernel_ms": (i32, [vp, fp]),
         "mm_sample": (i32, [vp, i32, i32, vp, i32, vp]),
         "mm_det_pow": (i32, [vp, vp, vp, i32, vp]),
+        "mm_selftest_div": (i32, [vp, i32, fp, C.POINTER(C.c_uint64)]),
         "mm_ipc_get_handle": (i32, [vp, vp, vp]),
         "mm_ipc_open_handle": (i32, [vp, vp, C.POINTER(vp)]),
         "mm_ipc_close_handle": (i32, [vp, vp]),

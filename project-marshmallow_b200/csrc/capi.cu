@@ -7,8 +7,8 @@
 //   descriptor set 0 image     -> pitch-linear float4 pointer (own, caller's or a peer GPU's) or a
 //                                 surface object over imported Vulkan memory
 //   vkCmdDispatch + submit     -> one kernel launch on the caller's stream
-// Memory plan per context: ~43 MB of read-only texture data (8+32 MB low-res, 1+4 MB placement,
-// <1 MB the rest), L2-resident on B200; output 16 B/pixel.
+// Memory plan per context: ~47 MB of read-only texture data (low-res volume 8 MB array + 32 MB
+// footprint-major copy, placement 1 + 4 MB, <1 MB the rest), L2-resident on B200; output 16 B/pixel.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -23,7 +23,7 @@ using namespace mm;
 struct TexSlot {
     cudaArray_t array = nullptr;
     cudaTextureObject_t obj = 0;
-    float4 *texels = nullptr;
+    uint4 *quads = nullptr;
     int w = 0, h = 0, d = 0;
     bool is3d = false;
 };
@@ -111,7 +111,7 @@ int mm_create(int device, mm_ctx **out) {
 static void free_slot(TexSlot &s) {
     if (s.obj) cudaDestroyTextureObject(s.obj);
     if (s.array) cudaFreeArray(s.array);
-    if (s.texels) cudaFree(s.texels);
+    if (s.quads) cudaFree(s.quads);
     s = TexSlot();
 }
 
@@ -140,7 +140,7 @@ int mm_destroy(mm_ctx *ctx) {
 }
 
 // Make the texels in device buffer `src` (uchar4, [z][y][x]) resident in slot `slot`: a cudaArray with
-// the reference's sampler state for hardware filtering, and the float4 copy for exact filtering.
+// the reference's sampler state for hardware filtering, and the footprint-major copy for exact filtering.
 static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, int d, bool is3d) {
     TexSlot &s = ctx->tex[slot];
     free_slot(s);
@@ -168,8 +168,8 @@ static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, i
     td.readMode = cudaReadModeNormalizedFloat;                                         // RGBA8_UNORM (Texture.h:29,85)
     td.normalizedCoords = 1;
     CU(cudaCreateTextureObject(&s.obj, &rd, &td, nullptr));
-    CU(cudaMalloc(&s.texels, n * sizeof(float4)));
-    CU(launch_unorm_to_float(src, s.texels, n, ctx->stream));
+    CU(cudaMalloc(&s.quads, n * sizeof(uint4)));
+    CU(launch_pack_quads(src, s.quads, w, h, d, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }
@@ -325,6 +325,19 @@ int mm_set_filter_mode(mm_ctx *ctx, int filter) {
     return MM_OK;
 }
 
+// CC:392-401: samples[i] = mat3(sun.directionBasis) * s_i, column-major, ((c0*x)+(c1*y))+(c2*z) per
+// component, binary32, no contraction (this file's host code is built with -ffp-contract=off).
+static void light_cone_samples(const float *sun, float out[18]) {
+    static const float sv[6][3] = {{0.f, 0.6f, 0.f}, {0.f, 0.5f, 0.05f}, {0.1f, 0.75f, 0.f}, {0.2f, 2.5f, 0.3f}, {0.f, 6.f, 0.f}, {-0.1f, 1.f, -0.2f}};
+    const float *c0 = sun + 12, *c1 = sun + 16, *c2 = sun + 20;
+    for (int i = 0; i < 6; i++)
+        for (int r = 0; r < 3; r++) {
+            volatile float a = c0[r] * sv[i][0], b = c1[r] * sv[i][1], c = c2[r] * sv[i][2];
+            volatile float ab = a + b;
+            out[3 * i + r] = ab + c;
+        }
+}
+
 int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream_v) {
     if (!ctx) return MM_ERR_ARG;
     if (mode != MM_FULL && mode != MM_PHASE16) return fail(ctx, MM_ERR_ARG, "mm_dispatch: unknown mode %d", mode);
@@ -333,7 +346,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     if (!ctx->out && !ctx->surf) return fail(ctx, MM_ERR_STATE, "mm_dispatch: no output image bound");
     static const int need[4] = {MM_TEX_PLACEMENT, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES};
     for (int i = 0; i < 4; i++)
-        if (!ctx->tex[need[i]].texels) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
+        if (!ctx->tex[need[i]].quads) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
 
@@ -341,9 +354,10 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     memcpy(p.cam, ctx->cam, sizeof p.cam);
     memcpy(p.sun, ctx->sun, sizeof p.sun);
     memcpy(p.sky, ctx->sky, sizeof p.sky);
+    light_cone_samples(ctx->sun, p.light);
     for (int i = 0; i < TEX_COUNT; i++) {
         const TexSlot &s = ctx->tex[i];
-        p.tex[i].texels = s.texels; p.tex[i].obj = s.obj;
+        p.tex[i].quads = s.quads; p.tex[i].obj = s.obj;
         p.tex[i].w = s.w; p.tex[i].h = s.h; p.tex[i].d = s.d;
         p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
     }
@@ -442,20 +456,35 @@ int mm_read_counters(mm_ctx *ctx, uint32_t *host_out) {
 
 int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, float *out_host) {
     if (!ctx || !uvw_host || !out_host || n < 0) return MM_ERR_ARG;
-    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].texels) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
+    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].quads) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
     if (filter != MM_FILTER_EXACT && filter != MM_FILTER_HW) return fail(ctx, MM_ERR_ARG, "mm_sample: filter must be EXACT or HW");
     CU(cudaSetDevice(ctx->device));
     float *duvw = nullptr; float4 *dout = nullptr;
     CU(cudaMalloc(&duvw, (size_t)n * 12 + 16));
     cudaError_t e = cudaMalloc(&dout, (size_t)n * 16 + 16);
     const TexSlot &s = ctx->tex[slot];
-    TexDev t = {s.texels, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
+    TexDev t = {s.quads, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
     if (e == cudaSuccess) e = cudaMemcpyAsync(duvw, uvw_host, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_sample_probe(t, s.is3d, filter, duvw, n, dout, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(duvw); cudaFree(dout);
     if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_sample: %s", cudaGetErrorString(e));
+    return MM_OK;
+}
+
+int mm_selftest_div(mm_ctx *ctx, int which, float *constant_out, unsigned long long *mismatches_out) {
+    if (!ctx || !constant_out || !mismatches_out) return MM_ERR_ARG;
+    if (which < 0 || which >= selftest_div_count()) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr;
+    CU(cudaMalloc(&d, 8));
+    cudaError_t e = cudaMemsetAsync(d, 0, 8, ctx->stream);
+    if (e == cudaSuccess) e = launch_selftest_div(which, constant_out, d, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mismatches_out, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_selftest_div: %s", cudaGetErrorString(e));
     return MM_OK;
 }
 

@@ -6,12 +6,12 @@
 
 namespace mm {
 
-// One bound texture.  `texels` is the EXACT-mode copy: one float4 per texel holding byte/255.0f
-// (IEEE divide, done once at upload), x fastest.  `obj` is the hardware-filtered view of the same
-// bytes: uchar4 cudaArray, normalised coordinates, wrap addressing, linear filter, UNORM -> float
+// One bound texture.  `quads` is the EXACT-mode copy: one uint4 per texel holding the 2x2 bilinear
+// footprint of packed RGBA8 words (wrap baked in), x fastest.  `obj` is the hardware-filtered view of
+// the same bytes: uchar4 cudaArray, normalised coordinates, wrap addressing, linear filter, UNORM -> float
 // (the reference sampler: Texture.cpp:29-52, 315-338).
 struct TexDev {
-    const float4 *texels;
+    const uint4 *quads;          // EXACT-mode copy, footprint-major (cloud_march.cu, "Sampler")
     cudaTextureObject_t obj;
     int w, h, d;
     int pow2;   // all extents are powers of two -> wrap by mask
@@ -25,6 +25,8 @@ struct MarchParams {
     float cam[40];   // UniformCameraObject (Shader.h:24-29)
     float sun[29];   // UniformSunObject    (SkyManager.h:8-14)
     float sky[13];   // UniformSkyObject    (SkyManager.h:28-36)
+    float light[18]; // the six cone-sample offsets mat3(sun.directionBasis) * s_i (CC:392-401): uniform per launch,
+                     // evaluated once on the host in the same binary32 order (capi.cu, light_cone_samples)
     TexDev tex[TEX_COUNT];
     float *out;                  // pitch-linear float4 image (may be peer memory), or nullptr when surf is used
     size_t pitch;                // bytes
@@ -40,7 +42,9 @@ struct MarchParams {
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
 cudaError_t launch_det_pow(const float *x, const float *y, int n, float *out, cudaStream_t stream);
-cudaError_t launch_unorm_to_float(const uchar4 *src, float4 *dst, size_t n, cudaStream_t stream);
+cudaError_t launch_pack_quads(const uchar4 *src, uint4 *dst, int w, int h, int d, cudaStream_t stream);
+int selftest_div_count();
+cudaError_t launch_selftest_div(int which, float *c_out, unsigned long long *mismatches_dev, cudaStream_t stream);
 cudaError_t launch_tonemap(const float *src, size_t pitch, int W, int H, uchar4 *dst, cudaStream_t stream);
 cudaError_t launch_curl_noise(uchar4 *dst128x128, float *scratch /* 15*128*128 + 8 floats */, const unsigned char *gradient_table /* 26^3, device */, cudaStream_t stream);
 cudaError_t launch_noise_volumes(uint32_t seed, uchar4 *low128, uchar4 *hi32, cudaStream_t stream);

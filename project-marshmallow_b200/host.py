@@ -146,7 +146,10 @@ class ComputeShader:
         self._check(self._lib.mm_set_filter_mode(self._ctx, mode))
 
     def dispatch(self, mode=capi.MM_FULL, row_begin=0, row_stride=1, row_block=1, stream=None):
-        self._check(self._lib.mm_dispatch(self._ctx, mode, row_begin, row_stride, row_block, C.c_void_p(stream) if stream else None))
+        """stream: None -> the context's own stream; an integer cudaStream_t otherwise (0, the legacy default
+        stream that torch calls its default stream, is passed as cudaStreamLegacy = 1)."""
+        sp = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        self._check(self._lib.mm_dispatch(self._ctx, mode, row_begin, row_stride, row_block, sp))
 
     def synchronize(self):
         self._check(self._lib.mm_synchronize(self._ctx))
@@ -188,6 +191,14 @@ class ComputeShader:
         out = np.empty((uvw.shape[0], 4), np.float32)
         self._check(self._lib.mm_sample(self._ctx, slot, filter_mode, _ptr(uvw), uvw.shape[0], _ptr(out)))
         return out
+
+    def selftestDiv(self, which):
+        c, bad = C.c_float(), C.c_uint64()
+        rc = self._lib.mm_selftest_div(self._ctx, which, C.byref(c), C.byref(bad))
+        if rc == -1:
+            return None
+        self._check(rc)
+        return c.value, bad.value
 
     def detPow(self, x, y):
         x, y = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(y, np.float32)

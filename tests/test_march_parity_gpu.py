@@ -179,3 +179,20 @@ def test_exact_sampler_bit_exact_on_gpu(mm, oracle, assets):
         hw = cs.sample(slot, mm.MM_FILTER_HW, uvw)
         assert np.abs(hw - want).max() < 1.0 / 256 + 1e-3      # 8-bit weights: close, not equal
     cs.close()
+
+
+def test_exact_divide_by_constant_is_the_ieee_quotient(mm):
+    """The march divides by literal constants through a 3-instruction exact sequence (csrc/cloud_march.cu,
+    div_const).  Exhaustive: every binary32 dividend, every constant in use, zero mismatching bit patterns."""
+    cs = mm.ComputeShader(0, (8, 8))
+    which, seen = 0, []
+    while True:
+        r = cs.selftestDiv(which)
+        if r is None:
+            break
+        c, bad = r
+        seen.append(c)
+        assert bad == 0, f"div_const(x, {c!r}) differs from x / {c!r} for {bad} dividends"
+        which += 1
+    cs.close()
+    assert len(seen) >= 10
