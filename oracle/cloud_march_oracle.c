@@ -204,7 +204,7 @@ struct om_scene {
     int pow_mode;    /* OM_POW_*    */
 };
 
-typedef struct { uint32_t trips, n2d, n3d, lit; } px_counters;
+typedef struct { uint32_t trips, n2d, n3d, lit; uint32_t *litmask; /* optional: bit k set = loop iteration k was a lit step (k < 256) */ } px_counters;
 
 typedef struct {
     const struct om_scene *s;
@@ -542,6 +542,7 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
             density = cloudHiRes(&cx, add3(currentPos, windOffset), stepSize, density, rHeight);       /* CC:436 (Q9) */
             if (density < 0.0001f) continue;                                      /* CC:437 (Q3) */
             cnt->lit++;
+            if (cnt->litmask && cnt->trips - 1 < 256) cnt->litmask[(cnt->trips - 1) >> 5] |= 1u << ((cnt->trips - 1) & 31);
             float densityAlongLight = 0.0f;
             for (int i = 0; i < 6; i++) {                                         /* CC:441-453 */
                 v3 lsPos = add3(currentPos, scale3(3.0f * stepSize, samples[i]));
@@ -606,6 +607,9 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
  * Pixels that are not written keep whatever `out` held (imageStore semantics).
  * counters (optional): 4 uint32 per pixel {loop trips, 2D fetches, 3D fetches, lit steps}.
  */
+static uint32_t *g_litmask = NULL;   /* diagnostics: 8 x uint32 per pixel, set with om_set_litmask_buffer */
+void om_set_litmask_buffer(uint32_t *buf) { g_litmask = buf; }
+
 int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_stride, int row_block,
              float *out_rgba32f, uint32_t *counters, int nthreads) {
     if (!s || !out_rgba32f || W <= 0 || H <= 0) return -1;
@@ -627,7 +631,7 @@ int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_s
         if (mode == OM_PHASE16 && (y % 4) != oy) continue;
         for (int x = 0; x < W; x++) {
             if (mode == OM_PHASE16 && (x % 4) != ox) continue;
-            px_counters c = {0, 0, 0, 0};
+            px_counters c = {0, 0, 0, 0, g_litmask ? g_litmask + 8 * ((size_t)y * W + x) : NULL};
             float o[4];
             march_pixel(s, x, y, W, H, o, &c);
             size_t i = (size_t)y * W + x;
