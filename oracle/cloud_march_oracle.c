@@ -385,6 +385,12 @@ static float cloudHiRes(const ctx_t *cx, v3 pos, float curlStrength, float origD
     return remapClampedf(origDensity, 1.0f * erosion, 1.0f, 0.0f, 1.0f);
 }
 
+/* diagnostics: how cloudTest calls end (never read by the march) */
+unsigned long long om_debug_stats[8];
+static int g_stats_on = 0;
+void om_debug_stats_enable(int on) { g_stats_on = on; if (on) memset(om_debug_stats, 0, sizeof om_debug_stats); }
+#define STAT(i) do { if (g_stats_on) { _Pragma("omp atomic") om_debug_stats[i]++; } } while (0)
+
 /* CC:231-253 (Q2: heightBiasCoverage called with swapped arguments) */
 static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     const struct om_scene *s = cx->s;
@@ -398,13 +404,19 @@ static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     cx->cnt->n3d++;
 
     float density = layerDensity * remapClampedf(dn[0], 0.3f, 1.0f, 0.0f, 1.0f);
+    STAT(0);
+    if (layerDensity == 0.0f) STAT(1);
+    else if (density < 0.0001f) STAT(2);
     if (density < 0.0001f) return 0.0f;
 
     float coverage = heightBiasCoverage(s, relativeHeight, ominf(0.85f, ci[0]));
+    int k_is_one = !(ci[0] > 0.7f);
 
     float erosion = ((0.625f * dn[1]) + (0.25f * dn[2])) + (0.125f * dn[3]);
     erosion = remapClampedf(erosion, coverage, 1.0f, 0.0f, 1.0f);
     density = remapClampedf(density, erosion, 1.0f, 0.0f, 1.0f);
+    if (density > 0.0f) STAT(4); else STAT(3);
+    if (k_is_one) STAT(5);
     return density;
 }
 

@@ -18,7 +18,7 @@ HEADERS = ["csrc/common.h", "../include/marshmallow.h", "host/SkyManager.h", "ho
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--cudart", "static"]
+          "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden", "--cudart", "static"] + os.environ.get("MM_NVCC_EXTRA", "").split()
 
 
 def _stale():

@@ -7,8 +7,9 @@
 //   descriptor set 0 image     -> pitch-linear float4 pointer (own, caller's or a peer GPU's) or a
 //                                 surface object over imported Vulkan memory
 //   vkCmdDispatch + submit     -> one kernel launch on the caller's stream
-// Memory plan per context: ~47 MB of read-only texture data (low-res volume 8 MB array + 32 MB
-// footprint-major copy, placement 1 + 4 MB, <1 MB the rest), L2-resident on B200; output 16 B/pixel.
+// Memory plan per context: ~83 MB of read-only texture data (low-res volume: 8 MB cudaArray + 64 MB
+// pair-major float copy; placement 1 + 8 MB; curl, hi-res ~2 MB), mostly L2-resident on B200 (126 MB),
+// HBM behind it; output 16 B/pixel.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -23,7 +24,7 @@ using namespace mm;
 struct TexSlot {
     cudaArray_t array = nullptr;
     cudaTextureObject_t obj = 0;
-    uint4 *quads = nullptr;
+    float4 *pairs = nullptr;      // EXACT-mode pair-major copy (not kept for the night-sky map)
     int w = 0, h = 0, d = 0;
     bool is3d = false;
 };
@@ -111,7 +112,7 @@ int mm_create(int device, mm_ctx **out) {
 static void free_slot(TexSlot &s) {
     if (s.obj) cudaDestroyTextureObject(s.obj);
     if (s.array) cudaFreeArray(s.array);
-    if (s.quads) cudaFree(s.quads);
+    if (s.pairs) cudaFree(s.pairs);
     s = TexSlot();
 }
 
@@ -140,7 +141,7 @@ int mm_destroy(mm_ctx *ctx) {
 }
 
 // Make the texels in device buffer `src` (uchar4, [z][y][x]) resident in slot `slot`: a cudaArray with
-// the reference's sampler state for hardware filtering, and the footprint-major copy for exact filtering.
+// the reference's sampler state for hardware filtering, and the pair-major float copy for exact filtering.
 static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, int d, bool is3d) {
     TexSlot &s = ctx->tex[slot];
     free_slot(s);
@@ -168,8 +169,8 @@ static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, i
     td.readMode = cudaReadModeNormalizedFloat;                                         // RGBA8_UNORM (Texture.h:29,85)
     td.normalizedCoords = 1;
     CU(cudaCreateTextureObject(&s.obj, &rd, &td, nullptr));
-    CU(cudaMalloc(&s.quads, n * sizeof(uint4)));
-    CU(launch_pack_quads(src, s.quads, w, h, d, ctx->stream));
+    CU(cudaMalloc(&s.pairs, n * 2 * sizeof(float4)));
+    CU(launch_pack_pairs(src, s.pairs, w, h, d, slot == MM_TEX_PLACEMENT, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }
@@ -346,7 +347,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     if (!ctx->out && !ctx->surf) return fail(ctx, MM_ERR_STATE, "mm_dispatch: no output image bound");
     static const int need[4] = {MM_TEX_PLACEMENT, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES};
     for (int i = 0; i < 4; i++)
-        if (!ctx->tex[need[i]].quads) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
+        if (!ctx->tex[need[i]].pairs) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
 
@@ -357,7 +358,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     light_cone_samples(ctx->sun, p.light);
     for (int i = 0; i < TEX_COUNT; i++) {
         const TexSlot &s = ctx->tex[i];
-        p.tex[i].quads = s.quads; p.tex[i].obj = s.obj;
+        p.tex[i].pairs = s.pairs; p.tex[i].obj = s.obj;
         p.tex[i].w = s.w; p.tex[i].h = s.h; p.tex[i].d = s.d;
         p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
     }
@@ -456,16 +457,16 @@ int mm_read_counters(mm_ctx *ctx, uint32_t *host_out) {
 
 int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, float *out_host) {
     if (!ctx || !uvw_host || !out_host || n < 0) return MM_ERR_ARG;
-    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].quads) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
+    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].pairs) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
     if (filter != MM_FILTER_EXACT && filter != MM_FILTER_HW) return fail(ctx, MM_ERR_ARG, "mm_sample: filter must be EXACT or HW");
     CU(cudaSetDevice(ctx->device));
     float *duvw = nullptr; float4 *dout = nullptr;
     CU(cudaMalloc(&duvw, (size_t)n * 12 + 16));
     cudaError_t e = cudaMalloc(&dout, (size_t)n * 16 + 16);
     const TexSlot &s = ctx->tex[slot];
-    TexDev t = {s.quads, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
+    TexDev t = {s.pairs, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
     if (e == cudaSuccess) e = cudaMemcpyAsync(duvw, uvw_host, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = launch_sample_probe(t, s.is3d, filter, duvw, n, dout, ctx->stream);
+    if (e == cudaSuccess) e = launch_sample_probe(t, s.is3d, slot == MM_TEX_PLACEMENT, filter, duvw, n, dout, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(duvw); cudaFree(dout);

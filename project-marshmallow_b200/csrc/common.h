@@ -6,12 +6,12 @@
 
 namespace mm {
 
-// One bound texture.  `quads` is the EXACT-mode copy: one uint4 per texel holding the 2x2 bilinear
-// footprint of packed RGBA8 words (wrap baked in), x fastest.  `obj` is the hardware-filtered view of
+// One bound texture.  `pairs` is the EXACT-mode copy: per texel two float4 {A(x),B(x),A(x+1),B(x+1)} for
+// the channel pairs (A,B), texel values 0..255 as binary32, wrap baked in, x fastest.  `obj` is the hardware-filtered view of
 // the same bytes: uchar4 cudaArray, normalised coordinates, wrap addressing, linear filter, UNORM -> float
 // (the reference sampler: Texture.cpp:29-52, 315-338).
 struct TexDev {
-    const uint4 *quads;          // EXACT-mode copy, footprint-major (cloud_march.cu, "Sampler")
+    const float4 *pairs;         // EXACT-mode copy, pair-major: 2 float4 per texel (cloud_march.cu, "Sampler")
     cudaTextureObject_t obj;
     int w, h, d;
     int pow2;   // all extents are powers of two -> wrap by mask
@@ -40,9 +40,9 @@ struct MarchParams {
 };
 
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);
-cudaError_t launch_sample_probe(const TexDev &t, int is3d, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
+cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
 cudaError_t launch_det_pow(const float *x, const float *y, int n, float *out, cudaStream_t stream);
-cudaError_t launch_pack_quads(const uchar4 *src, uint4 *dst, int w, int h, int d, cudaStream_t stream);
+cudaError_t launch_pack_pairs(const uchar4 *src, float4 *dst, int w, int h, int d, int placement_layout, cudaStream_t stream);
 int selftest_div_count();
 cudaError_t launch_selftest_div(int which, float *c_out, unsigned long long *mismatches_dev, cudaStream_t stream);
 cudaError_t launch_tonemap(const float *src, size_t pitch, int W, int H, uchar4 *dst, cudaStream_t stream);
