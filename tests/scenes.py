@@ -29,6 +29,18 @@ def constant_placement(r, b, size=64):
     return t
 
 
+def synthetic_night_sky(w=96, h=64):
+    """A small non-power-of-two star map for the night branch (the shipped 1920x1080 nightSky_noOrange.png is 8 MB
+    decoded and is not needed to exercise CC:365-384; REPEAT wrap on non-power-of-two extents is)."""
+    rng = np.random.default_rng(42)
+    t = np.zeros((h, w, 4), np.uint8)
+    t[..., :3] = rng.integers(0, 40, (h, w, 3))
+    stars = rng.random((h, w)) > 0.97
+    t[stars, :3] = rng.integers(150, 256, (int(stars.sum()), 3))
+    t[..., 3] = 255
+    return t
+
+
 CONFIGS = {
     # name: (W, H, camera pos, yaw, pitch(rad, negative looks up), elevation, azimuth, wind xyz, time, placement)
     "C1": dict(W=320, H=180, pos=(0.0, 1.0, 1.0), yaw=-np.pi / 2, pitch=-20 * DEG2RAD, elevation=0.25, azimuth=0.25,

@@ -1,0 +1,54 @@
+"""Host-side value producers (mm_host_sky / mm_host_camera, CPU only) against hand-derived values of the
+reference formulas (SkyManager.cpp:15-70, camera.cpp:27-39,179-195, camera.h:72)."""
+import numpy as np
+import pytest
+
+
+def test_sun_at_zenith(mm):
+    sun, sky = mm.host_sky(0.25, 0.25)
+    d = sun[4:7]
+    assert d[1] == pytest.approx(1.0, abs=1e-6) and abs(d[0]) < 1e-6 and abs(d[2]) < 1e-6
+    assert sun[28] == pytest.approx(1000 * (1 - np.exp(-(1.6110731557 - 0.0) / 1.5)), rel=1e-5)      # 658.4
+    assert np.allclose(sun[8:11], 1.0)                         # white at dir.y >= 1/13
+    assert np.allclose(sun[0:3], 400000.0 * d, rtol=1e-6) and sun[3] == 1.0
+    assert np.allclose(sun[16:19], d)                          # directionBasis column 1 = direction (CC:324)
+    basis = sun[12:24].reshape(3, 4)[:, :3]
+    assert np.allclose(basis @ basis.T, np.eye(3), atol=1e-5)  # orthonormal TBN
+    assert sky[12] == pytest.approx(0.8) and np.allclose(sky[8:11], [1, 0.05, 1]) and sky[11] == 0.0
+    # betaR = RAYLEIGH_TOTAL * (rayleigh - 1 + sunFade), sunFade = 1 - clamp(1 - exp(400000/450000), 0, 1) = 1
+    assert np.allclose(sky[0:3], np.array([5.804542996261093e-6, 1.3562911419845635e-5, 3.0265902468824876e-5]) * 2.0, rtol=1e-5)
+    assert np.allclose(sky[4:7], 0.434 * (0.2 * 10 * 10e-18) * np.array([1.839991851443397, 2.779802391966052, 4.079047954386109]) * 0.005, rtol=1e-5)
+
+
+def test_low_sun_colour_and_intensity(mm):
+    sun, _ = mm.host_sky(0.008, 0.25)                          # config C3
+    dy = sun[5]
+    assert dy == pytest.approx(np.sin(2 * np.pi * 0.008), rel=1e-3)
+    t = min(max(dy * 13, 0), 1)
+    assert np.allclose(sun[8:11], (1 - t) * np.array([2.0, 0.33922, 0.0431]) + t, rtol=1e-5)
+    assert sun[28] == pytest.approx(1000 * max(0, 1 - np.exp(-(1.6110731557 - np.arccos(dy)) / 1.5)), rel=1e-4)
+    assert sun[6] > 0.99                                       # towards +z
+
+
+def test_night_sun(mm):
+    sun, _ = mm.host_sky(0.75, 0.25)
+    assert sun[5] < 0 and sun[28] == 2.0 and np.allclose(sun[8:11], [0.8, 0.9, 1.0])
+    assert sun[17] == pytest.approx(-sun[5], abs=1e-6)          # basis negated below the horizon
+    assert sun[1] > 0                                          # location flipped above the horizon
+
+
+def test_pixel_phase_and_time(mm):
+    sun, sky = mm.host_sky(0.25, 0.25, time=12.5, pixel_phase=21)
+    assert sun[11] == 5.0 and sky[11] == 12.5                  # (a+1)%16 bookkeeping lives in sun.color.a (VA:384)
+
+
+def test_camera_block(mm):
+    cam = mm.host_camera((0, 1, 1), -np.pi / 2, -20 * 0.01745)
+    view = cam[:16].reshape(4, 4).T                            # row-major view of the column-major block
+    R = view[:3, :3]
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-6)
+    fwd = R[2]                                                 # third row = m_forward; the camera looks along -forward
+    assert np.allclose(-fwd, [0, np.sin(20 * 0.01745), np.cos(20 * 0.01745)], atol=1e-6)
+    assert np.allclose(cam[32:36], [0, 1, 1, 1])
+    assert cam[36] == pytest.approx(1920 / 1080) and cam[37] == pytest.approx(np.tan(0.5 * 0.01745 * 45), rel=1e-6)
+    assert np.allclose(view[:3, 3], -R @ np.array([0, 1, 1]), atol=1e-6)

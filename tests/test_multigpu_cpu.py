@@ -1,0 +1,81 @@
+"""Host-side logic of the multi-GPU path on CPU: the row-cyclic partition and the handle exchange over a
+world_size-2 gloo process group (the kernels' half of the contract is tested on the GPU by
+test_row_partition_union_equals_full_frame)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+
+def test_partition_is_an_exact_cover(mm):
+    for H in (1, 7, 117, 1080, 2160):
+        for world in (1, 2, 3, 8):
+            for block in (1, 2, 4, 16):
+                assert mm.multigpu.partition_is_exact_cover(H, world, block), (H, world, block)
+
+
+def test_partition_matches_oracle_dispatch(mm, oracle, assets):
+    """owned_rows() == the rows the oracle's row partition writes (same rule as mm_dispatch)."""
+    import scenes
+    W, H = 24, 37
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    for world, block in ((2, 1), (3, 2), (4, 4)):
+        for r in range(world):
+            out, _ = S.march(W, H, row_begin=r, row_stride=world, row_block=block, counters=False, out=np.full((H, W, 4), -7, np.float32))
+            rows = np.nonzero((out != -7).any(axis=(1, 2)))[0]
+            assert np.array_equal(rows, mm.multigpu.owned_rows(H, r, world, block))
+
+
+def test_row_cyclic_balances_load_better_than_bands(mm, oracle, assets):
+    """rows below the horizon are free, so contiguous bands are badly unbalanced; row-cyclic is not."""
+    import scenes
+    W, H = 160, 90
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    _, cnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"]).march(W, H)
+    row_cost = (cnt[..., 1] + 2 * cnt[..., 2]).sum(axis=1).astype(np.float64)
+    n = 8
+    cyc = [row_cost[mm.multigpu.owned_rows(H, r, n, 2)].sum() for r in range(n)]
+    band = [c.sum() for c in np.array_split(row_cost, n)]
+    eff = lambda parts: np.mean(parts) / np.max(parts)
+    assert eff(cyc) > 0.85 and eff(cyc) > eff(band) + 0.2
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    sys.path.insert(0, {root!r})
+    import torch.distributed as dist
+    import _pkg
+    mm = _pkg.load_package()
+    dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=2)
+    rank = dist.get_rank()
+    handle = bytes(range(64)) if rank == 0 else None
+    got = mm.multigpu.exchange_handle(handle, rank, 2, dist)
+    assert got == bytes(range(64)), got
+    rows = mm.multigpu.owned_rows(37, rank, 2, 2)
+    gathered = [None, None]
+    dist.all_gather_object(gathered, rows.tolist())
+    assert sorted(gathered[0] + gathered[1]) == list(range(37))
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+""")
+
+
+def test_handle_exchange_over_gloo_world_size_2(tmp_path):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=root))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=180)
+        assert p.returncode == 0, out
+        assert "ok" in out
