@@ -172,6 +172,10 @@ class ComputeShader:
         self._check(self._lib.mm_read_output(self._ctx, _ptr(out)))
         return out
 
+    def readOutputInto(self, out):
+        self._check(self._lib.mm_read_output(self._ctx, _ptr(out)))
+        return out
+
     def tonemapRGBA8(self):
         out = np.empty((self.height, self.width, 4), np.uint8)
         self._check(self._lib.mm_tonemap_rgba8(self._ctx, _ptr(out), 0, None))
