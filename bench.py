@@ -12,7 +12,7 @@ between timed frames by writing a 256 MB buffer (config.l2: "flushed"); each fra
 CUDA event pair on the launching stream and the flush is outside the pairs.
 
 N > 1 (torchrun, one process per GPU): STRONG scaling -- the same frame is sharded row-cyclically
-(row block 2) over the ranks; every rank's kernel stores its pixels straight into rank 0's image over
+(row block 4 = the height of a warp tile) over the ranks; every rank's kernel stores its pixels straight into rank 0's image over
 NVLink (CUDA-IPC mapped peer memory), so there is no separate gather collective.  Time = max over ranks.
 """
 import argparse
@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--filter", default="hybrid", choices=["exact", "hw", "hybrid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--row-block", type=int, default=2)
+    ap.add_argument("--row-block", type=int, default=4)
     return ap.parse_args()
 
 
@@ -267,6 +267,16 @@ def main():
                                "traffic": None, "Q_quads_per_pixel": wq["Q"], "loop_trips_per_pixel": wq["trips"], "lit_steps_per_pixel": wq["lit"],
                                "peak_source": f"148 SM x 4 bilinear quads/clk x sm_max_mhz ({which} clock); algorithmic quads from the oracle's fetch counters",
                                "hbm_floor_ms": W * H * 16 / (peaks["hbm_gbs"] * 1e9) * 1e3}
+            # second roofline: the march is FP32 / instruction-issue bound.  Warp-instructions per frame of this
+            # exact command come from the committed ncu capture (profiles/); peak = 148 SM x 4 schedulers x f_SM.
+            prof = os.path.join(ROOT, "profiles", f"r01_final_{args.filter}.summary.csv")
+            if os.path.exists(prof) and args.config == "C2" and world == 1:
+                winst = [float(l.split(",")[2]) for l in open(prof) if l.startswith("smsp__inst_executed.sum,")]
+                if winst:
+                    peak_issue = N_SM * 4 * peaks["sm_max_mhz"] * 1e6
+                    out["roofline_issue"] = {"bound": "instruction issue (FP32)", "achieved": winst[0] / (ms * 1e-3) / 1e9, "peak": peak_issue / 1e9,
+                                             "unit": "Gwarp-inst/s", "frac": winst[0] / (ms * 1e-3) / peak_issue,
+                                             "warp_instructions_per_frame": winst[0], "source": os.path.relpath(prof, ROOT)}
             v = wq["pixels"] / wq["seconds"] / 1e6
             out["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"every {rows_step}th row of the same frame ({wq['pixels']} px), oracle port with counters, OpenMP"}

@@ -11,9 +11,10 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmarshmallow_b200.so")
+DEMO = os.path.join(HERE, "frame_demo")
 CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu"]
 CPP_SOURCES = ["host/sky_camera.cpp"]
-HEADERS = ["csrc/common.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h"]
+HEADERS = ["csrc/common.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h", "host/ComputeShader.h", "host/frame_demo.cpp"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -51,6 +52,9 @@ def build_library(force=False, verbose=False, ptxas_v=False):
         raise RuntimeError("nvcc failed")
     cmd = [NVCC] + ARCH + ["-shared", "--cudart", "static", "-o", LIB] + objs
     subprocess.run(cmd, check=True)
+    # the headless C++ host demo (host/frame_demo.cpp) over the C++ mirror classes
+    subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", DEMO, os.path.join(HERE, "host", "frame_demo.cpp"),
+                    "-L" + HERE, "-lmarshmallow_b200", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

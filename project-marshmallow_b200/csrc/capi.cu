@@ -10,6 +10,7 @@
 // Memory plan per context: ~83 MB of read-only texture data (low-res volume: 8 MB cudaArray + 64 MB
 // pair-major float copy; placement 1 + 8 MB; curl, hi-res ~2 MB), mostly L2-resident on B200 (126 MB),
 // HBM behind it; output 16 B/pixel.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -339,6 +340,30 @@ static void light_cone_samples(const float *sun, float out[18]) {
         }
 }
 
+// Order the 8-row block rows of one dispatch by expected cost, descending.  Cost proxy: the ray through the
+// middle column of the block row's middle row; below the horizon (CC:351) it is free, otherwise the path
+// through the shell grows as the ray approaches the horizon, i.e. as rd.y falls.  Scheduling hint only.
+static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows) {
+    const float *cam = p.cam;
+    struct Key { float k; uint16_t i; };
+    static thread_local Key keys[1024];
+    for (int b = 0; b < nblockrows; b++) {
+        int j = b * 8 + 4, py;
+        if (p.mode == DISPATCH_PHASE16) py = j * 4;
+        else { int k = j / p.row_block; py = (p.row_begin + k * p.row_stride) * p.row_block + (j - k * p.row_block); }
+        if (py >= p.H) py = p.H - 1;
+        double spy = 2.0 * py / p.H - 1.0;
+        double tanH = cam[37];
+        // rd ~ -look - spy*tanH*up (middle column: spx = 0); only the sign and size of its y matter
+        double dx = -cam[2] - spy * tanH * cam[1], dy = -cam[6] - spy * tanH * cam[5], dz = -cam[10] - spy * tanH * cam[9];
+        double y = dy / std::sqrt(dx * dx + dy * dy + dz * dz);
+        keys[b].k = y < 0.0 ? 2.0f : (float)y;       // ascending key = descending cost; below-horizon rows last
+        keys[b].i = (uint16_t)b;
+    }
+    std::stable_sort(keys, keys + nblockrows, [](const Key &a, const Key &b) { return a.k < b.k; });
+    for (int b = 0; b < nblockrows; b++) order[b] = keys[b].i;
+}
+
 int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream_v) {
     if (!ctx) return MM_ERR_ARG;
     if (mode != MM_FULL && mode != MM_PHASE16) return fail(ctx, MM_ERR_ARG, "mm_dispatch: unknown mode %d", mode);
@@ -375,6 +400,9 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         p.owned_rows = (ctx->H + 3) / 4;
         p.grid_w = (ctx->W + 3) / 4;
     }
+    int nblockrows = (p.owned_rows + 7) / 8;
+    if (nblockrows > 1024) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: more than 8192 rows per dispatch");
+    order_block_rows(p, p.block_row_order, nblockrows);
     CU(cudaEventRecord(ctx->ev0, stream));
     CU(launch_cloud_march(p, ctx->filter, stream));
     CU(cudaEventRecord(ctx->ev1, stream));

@@ -37,6 +37,11 @@ struct MarchParams {
     int row_begin, row_stride, row_block;
     int owned_rows;              // rows this dispatch enumerates (FULL), virtual rows (PHASE16)
     int grid_w;                  // pixel columns enumerated (W, or ceil(W/4) in PHASE16)
+    // Execution order of the 8-row block rows, most expensive first (rays nearest the horizon cross the longest
+    // stretch of the cloud shell; rays below it are free): blockIdx.y -> block row.  Keeps the tail of the launch
+    // cheap, which is what limits strong scaling when a GPU owns only a few waves of tiles.  Built on the host
+    // per dispatch (capi.cu, order_block_rows); affects scheduling only, never results.
+    uint16_t block_row_order[1024];
 };
 
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);

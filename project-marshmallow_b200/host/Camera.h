@@ -5,7 +5,7 @@
 
 namespace marshmallow {
 
-class Camera {
+class MM_CXX_API Camera {
 public:
     Camera(const float position[3], float yaw, float pitch, float fovDeg = 45.0f, float aspect = 1920.0f / 1080.0f);
     void getView(float view16[16]) const;

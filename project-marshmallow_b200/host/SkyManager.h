@@ -5,7 +5,7 @@
 
 namespace marshmallow {
 
-class SkyManager {
+class MM_CXX_API SkyManager {
 public:
     SkyManager();
     void rebuildSkyFromNewSun(float elevation, float azimuth);

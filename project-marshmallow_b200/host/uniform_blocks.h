@@ -8,6 +8,10 @@
 #pragma once
 #include <cstddef>
 
+#ifndef MM_CXX_API
+#define MM_CXX_API __attribute__((visibility("default")))
+#endif
+
 namespace marshmallow {
 
 struct UniformCameraObject {

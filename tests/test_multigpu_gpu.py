@@ -28,7 +28,7 @@ WORKER = textwrap.dedent("""
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
     shared = mm.multigpu.SharedFrame(cs, rank, world, dist)
     dist.barrier()
-    cs.dispatch(mm.MM_FULL, rank, world, 2)
+    cs.dispatch(mm.MM_FULL, rank, world, 4)
     cs.synchronize()
     dist.barrier()
     if rank == 0:
