@@ -385,6 +385,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         const TexSlot &s = ctx->tex[i];
         p.tex[i].pairs = s.pairs; p.tex[i].obj = s.obj;
         p.tex[i].w = s.w; p.tex[i].h = s.h; p.tex[i].d = s.d;
+        p.tex[i].wf = (float)s.w; p.tex[i].hf = (float)s.h; p.tex[i].df = (float)s.d;
         p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
     }
     p.out = ctx->out; p.pitch = ctx->pitch; p.surf = ctx->surf;
@@ -492,7 +493,7 @@ int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, f
     CU(cudaMalloc(&duvw, (size_t)n * 12 + 16));
     cudaError_t e = cudaMalloc(&dout, (size_t)n * 16 + 16);
     const TexSlot &s = ctx->tex[slot];
-    TexDev t = {s.pairs, s.obj, s.w, s.h, s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
+    TexDev t = {s.pairs, s.obj, s.w, s.h, s.d, (float)s.w, (float)s.h, (float)s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
     if (e == cudaSuccess) e = cudaMemcpyAsync(duvw, uvw_host, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_sample_probe(t, s.is3d, slot == MM_TEX_PLACEMENT, filter, duvw, n, dout, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, dout, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);

@@ -14,6 +14,7 @@ struct TexDev {
     const float4 *pairs;         // EXACT-mode copy, pair-major: 2 float4 per texel (cloud_march.cu, "Sampler")
     cudaTextureObject_t obj;
     int w, h, d;
+    float wf, hf, df;   // the extents as binary32 (exact)
     int pow2;   // all extents are powers of two -> wrap by mask
 };
 

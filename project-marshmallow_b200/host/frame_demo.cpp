@@ -32,7 +32,7 @@ int main(int argc, char **argv) {
         computeShader.setFilterMode(filter);
 
         const float pos[3] = {0.0f, 1.0f, 1.0f};
-        Camera mainCamera(pos, -3.14159265f / 2.0f, -20.0f * 0.01745f);
+        Camera mainCamera(pos, (float)(-3.141592653589793 / 2.0), (float)(-20 * 0.01745));   // config C1 (tests/scenes.py)
         SkyManager skySystem;
         UniformCameraObject uco, ucoPrev;
         mainCamera.fillUniform(uco);
