@@ -92,11 +92,22 @@ static float perlin_fbm(float x, float y, float z, int cells, int octaves, uint3
 static inline float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 static inline uint8_t quant(float v) { return (uint8_t)(int)((clamp01(v) * 255.0f) + 0.5f); }
 
-/* constants chosen once so the channel statistics sit near the shipped volumes'  */
-#define NV_PW_GAIN   1.05f
-#define NV_PW_BIAS  -0.07f
-#define NV_W_GAIN    1.30f
-#define NV_W_BIAS    0.16f
+/* per-channel affine maps fitted once (seed 0) so that the channel means / standard deviations equal the shipped
+   volumes' (low-res mean .504 .686 .687 .687, std .105 .104 .102 .102; hi-res mean .687 .690 .685, std ~.10) */
+#define NV_L0_GAIN 0.8718f
+#define NV_L0_BIAS -0.1396f
+#define NV_L1_GAIN 0.8817f
+#define NV_L1_BIAS 0.2618f
+#define NV_L2_GAIN 0.8671f
+#define NV_L2_BIAS 0.2710f
+#define NV_L3_GAIN 0.8721f
+#define NV_L3_BIAS 0.2644f
+#define NV_H0_GAIN 0.9660f
+#define NV_H0_BIAS 0.2127f
+#define NV_H1_GAIN 0.8610f
+#define NV_H1_BIAS 0.2786f
+#define NV_H2_GAIN 0.8877f
+#define NV_H2_BIAS 0.2553f
 
 void om_noise_lowres_voxel(uint32_t seed, int x, int y, int z, uint8_t out[4]) {
     float px = ((float)x + 0.5f) * (1.0f / 128.0f), py = ((float)y + 0.5f) * (1.0f / 128.0f), pz = ((float)z + 0.5f) * (1.0f / 128.0f);
@@ -106,10 +117,10 @@ void om_noise_lowres_voxel(uint32_t seed, int x, int y, int z, uint8_t out[4]) {
     float w2 = worley_fbm(px, py, pz, 16, seed + 300u);
     float w3 = worley_fbm(px, py, pz, 32, seed + 400u);
     float pw = w0 + (clamp01(pf) * (1.0f - w0));                          /* remap(perlin, 0, 1, worley, 1) */
-    out[0] = quant((pw * NV_PW_GAIN) + NV_PW_BIAS);
-    out[1] = quant((w1 * NV_W_GAIN) + NV_W_BIAS);
-    out[2] = quant((w2 * NV_W_GAIN) + NV_W_BIAS);
-    out[3] = quant((w3 * NV_W_GAIN) + NV_W_BIAS);
+    out[0] = quant((pw * NV_L0_GAIN) + NV_L0_BIAS);
+    out[1] = quant((w1 * NV_L1_GAIN) + NV_L1_BIAS);
+    out[2] = quant((w2 * NV_L2_GAIN) + NV_L2_BIAS);
+    out[3] = quant((w3 * NV_L3_GAIN) + NV_L3_BIAS);
 }
 
 void om_noise_hires_voxel(uint32_t seed, int x, int y, int z, uint8_t out[4]) {
@@ -117,9 +128,9 @@ void om_noise_hires_voxel(uint32_t seed, int x, int y, int z, uint8_t out[4]) {
     float w0 = worley_fbm(px, py, pz, 2, seed + 500u);
     float w1 = worley_fbm(px, py, pz, 4, seed + 600u);
     float w2 = worley_fbm(px, py, pz, 8, seed + 700u);
-    out[0] = quant((w0 * NV_W_GAIN) + NV_W_BIAS);
-    out[1] = quant((w1 * NV_W_GAIN) + NV_W_BIAS);
-    out[2] = quant((w2 * NV_W_GAIN) + NV_W_BIAS);
+    out[0] = quant((w0 * NV_H0_GAIN) + NV_H0_BIAS);
+    out[1] = quant((w1 * NV_H1_GAIN) + NV_H1_BIAS);
+    out[2] = quant((w2 * NV_H2_GAIN) + NV_H2_BIAS);
     out[3] = 0;
 }
 

@@ -88,10 +88,21 @@ __device__ float perlin_fbm(float x, float y, float z, int cells, int octaves, u
 __device__ __forceinline__ float clamp01(float v) { return v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v); }
 __device__ __forceinline__ unsigned char quant(float v) { return (unsigned char)(int)((clamp01(v) * 255.0f) + 0.5f); }
 
-#define NV_PW_GAIN 1.05f
-#define NV_PW_BIAS -0.07f
-#define NV_W_GAIN 1.30f
-#define NV_W_BIAS 0.16f
+// per-channel affine maps fitted once (seed 0) to the shipped volumes' channel means / standard deviations
+#define NV_L0_GAIN 0.8718f
+#define NV_L0_BIAS -0.1396f
+#define NV_L1_GAIN 0.8817f
+#define NV_L1_BIAS 0.2618f
+#define NV_L2_GAIN 0.8671f
+#define NV_L2_BIAS 0.2710f
+#define NV_L3_GAIN 0.8721f
+#define NV_L3_BIAS 0.2644f
+#define NV_H0_GAIN 0.9660f
+#define NV_H0_BIAS 0.2127f
+#define NV_H1_GAIN 0.8610f
+#define NV_H1_BIAS 0.2786f
+#define NV_H2_GAIN 0.8877f
+#define NV_H2_BIAS 0.2553f
 
 __global__ void __launch_bounds__(128) lowres_kernel(uint32_t seed, uchar4 *out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
@@ -102,8 +113,8 @@ __global__ void __launch_bounds__(128) lowres_kernel(uint32_t seed, uchar4 *out)
     float w2 = worley_fbm(px, py, pz, 16, seed + 300u);
     float w3 = worley_fbm(px, py, pz, 32, seed + 400u);
     float pw = w0 + (clamp01(pf) * (1.0f - w0));
-    out[((size_t)z * 128 + y) * 128 + x] = make_uchar4(quant((pw * NV_PW_GAIN) + NV_PW_BIAS), quant((w1 * NV_W_GAIN) + NV_W_BIAS),
-                                                       quant((w2 * NV_W_GAIN) + NV_W_BIAS), quant((w3 * NV_W_GAIN) + NV_W_BIAS));
+    out[((size_t)z * 128 + y) * 128 + x] = make_uchar4(quant((pw * NV_L0_GAIN) + NV_L0_BIAS), quant((w1 * NV_L1_GAIN) + NV_L1_BIAS),
+                                                       quant((w2 * NV_L2_GAIN) + NV_L2_BIAS), quant((w3 * NV_L3_GAIN) + NV_L3_BIAS));
 }
 
 __global__ void __launch_bounds__(32) hires_kernel(uint32_t seed, uchar4 *out) {
@@ -112,8 +123,8 @@ __global__ void __launch_bounds__(32) hires_kernel(uint32_t seed, uchar4 *out) {
     float w0 = worley_fbm(px, py, pz, 2, seed + 500u);
     float w1 = worley_fbm(px, py, pz, 4, seed + 600u);
     float w2 = worley_fbm(px, py, pz, 8, seed + 700u);
-    out[((size_t)z * 32 + y) * 32 + x] = make_uchar4(quant((w0 * NV_W_GAIN) + NV_W_BIAS), quant((w1 * NV_W_GAIN) + NV_W_BIAS),
-                                                     quant((w2 * NV_W_GAIN) + NV_W_BIAS), 0);
+    out[((size_t)z * 32 + y) * 32 + x] = make_uchar4(quant((w0 * NV_H0_GAIN) + NV_H0_BIAS), quant((w1 * NV_H1_GAIN) + NV_H1_BIAS),
+                                                     quant((w2 * NV_H2_GAIN) + NV_H2_BIAS), 0);
 }
 
 }  // namespace
