@@ -129,7 +129,8 @@ def run_reference(args):
         "impl": "reference", "metric": "cloud-march throughput", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_full_frame_extrapolated": sc["W"] * sc["H"] / v / 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} {sc['W']}x{sc['H']} full-resolution cloud march, shipped textures"},
+        "config": {"workload": f"{args.config} {sc['W']}x{sc['H']} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
+                   "filter": "oracle FP32 sampler", "l2": "n/a (CPU)", "parallelism": f"{cores} host threads"},
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle port of compute-clouds.comp; stands in for the reference shader on lavapipe, which cannot run here"},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

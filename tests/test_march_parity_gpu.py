@@ -240,3 +240,48 @@ def test_size_independent_properties_at_8k(mm, assets):
     below = a[H - 64:]                     # the bottom rows look below the horizon in this view: no cloud, alpha = seed
     assert float(below[..., :3].min()) > 0.0
     cs.close()
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (17, 5), (33, 9), (130, 70)])
+def test_ragged_and_tiny_extents(mm, oracle, assets, W, H):
+    """Extents that are not multiples of the 16x8 block or the 4x4 phase grid, down to a single pixel."""
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    ref, rcnt = S.march(W, H)
+    img, cnt = _render(mm, sc, mm.MM_FILTER_EXACT)
+    rep = oracle.parity_report(ref, img, rcnt, cnt)
+    assert rep["counter_mismatch_pixels"] == 0 and rep["max_abs_diff_8bit"] <= 1, rep
+    # one reference-style phase dispatch on the same ragged extent
+    sc5 = scenes.make_scene(mm, "C1", assets, W=W, H=H, pixel_phase=6)
+    S5 = oracle.Scene(sc5["textures"], sc5["cam"], sc5["sun"], sc5["sky"])
+    sentinel = np.full((H, W, 4), -7.0, np.float32)
+    ref5, _ = S5.march(W, H, mode=oracle.OM_PHASE16, out=sentinel.copy())
+    import torch
+    t = torch.from_numpy(sentinel.copy()).cuda()
+    cs = mm.ComputeShader(0, (W, H), placement=sc5["textures"]["placement"], curl=sc5["textures"]["curl"],
+                          lowRes=sc5["textures"]["lowres"], hiRes=sc5["textures"]["hires"])
+    cs.bindOutput(t.data_ptr())
+    cs.updateUniformBuffers(sc5["cam"], None, sc5["sky"], sc5["sun"])
+    cs.dispatch(mm.MM_PHASE16)
+    cs.synchronize()
+    got = t.cpu().numpy()
+    cs.close()
+    assert ((got != -7.0).any(-1) == (ref5 != -7.0).any(-1)).all()
+    assert oracle.parity_report(ref5, got)["max_abs_diff_8bit"] <= 1
+
+
+def test_bad_arguments_are_rejected_on_gpu(mm, assets):
+    cs = mm.ComputeShader(0, (64, 36), placement=assets["placement"], curl=assets["curl"], lowRes=assets["lowres"], hiRes=assets["hires"])
+    cs.allocOutput()
+    sun, sky = mm.host_sky(0.25, 0.25)
+    cs.updateUniformBuffers(mm.host_camera((0, 1, 1), 0.0, 0.0), None, sky, sun)
+    for bad in ((7, 0, 1, 1), (0, -1, 1, 1), (0, 0, 0, 1), (0, 0, 1, 0)):
+        with pytest.raises(mm.MarshmallowError):
+            cs.dispatch(*bad)
+    with pytest.raises(mm.MarshmallowError):
+        cs.uploadTexture(mm.MM_TEX_LOWRES, assets["placement"])      # a 2D texture into a 3D sampler slot
+    with pytest.raises(mm.MarshmallowError):
+        cs.setFilterMode(9)
+    cs.dispatch()                                                     # still usable after the errors
+    cs.synchronize()
+    cs.close()
