@@ -104,7 +104,9 @@ MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int
 MM_API int mm_synchronize(mm_ctx *ctx);
 
 /* host-buffer convenience (the end-to-end call): uniforms in, march, image out to HOST memory.
- * out_host: w*h*4 floats (packed).  Includes H2D of the uniforms and D2H of the image. */
+ * out_host: w*h*4 floats (packed).  Includes H2D of the uniforms and D2H of the image.  When out_host is
+ * page-locked (cudaHostAlloc / cudaHostRegister) and mode is MM_FULL the D2H transfer is fused into the kernel
+ * (each pixel is stored to the device image and to out_host); otherwise the image is copied after the march. */
 MM_API int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, const void *sky52,
                              int mode, float *out_host_rgba32f);
 

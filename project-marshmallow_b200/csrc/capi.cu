@@ -45,6 +45,7 @@ struct mm_ctx {
     cudaExternalMemory_t ext_mem = nullptr;
     cudaMipmappedArray_t ext_mip = nullptr;
     cudaSurfaceObject_t surf = 0;
+    float *mirror = nullptr;       // set only for the duration of one mm_render_to_host dispatch
     uint32_t *counters = nullptr;
     bool counters_on = false;
     int filter = FILTER_EXACT;
@@ -389,6 +390,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
     }
     p.out = ctx->out; p.pitch = ctx->pitch; p.surf = ctx->surf;
+    p.mirror = ctx->mirror; p.mirror_pitch = (size_t)ctx->W * 16;
     p.counters = ctx->counters_on ? ctx->counters : nullptr;
     p.W = ctx->W; p.H = ctx->H; p.mode = mode;
     p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block;
@@ -441,9 +443,23 @@ int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, co
     int rc = mm_set_uniforms(ctx, camera160, nullptr, sun116, sky52);
     if (rc) return rc;
     if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_render_to_host: no linear output bound (mm_alloc_output)");
+    // Pinned (page-locked) destination + full frame: the kernel stores every finished pixel to the device image AND
+    // straight into the caller's buffer over PCIe, so the device->host transfer overlaps the march instead of following
+    // it.  Pageable destination or a 1/16 phase dispatch: march, then copy the image.
+    float *mapped = nullptr;
+    if (mode == MM_FULL) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out_host) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            mapped = static_cast<float *>(attr.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    ctx->mirror = mapped;
     rc = mm_dispatch(ctx, mode, 0, 1, 1, nullptr);
+    ctx->mirror = nullptr;
     if (rc) return rc;
-    CU(cudaMemcpy2DAsync(out_host, (size_t)ctx->W * 16, ctx->out, ctx->pitch, (size_t)ctx->W * 16, ctx->H, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!mapped)
+        CU(cudaMemcpy2DAsync(out_host, (size_t)ctx->W * 16, ctx->out, ctx->pitch, (size_t)ctx->W * 16, ctx->H, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }

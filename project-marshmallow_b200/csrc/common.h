@@ -31,6 +31,8 @@ struct MarchParams {
     TexDev tex[TEX_COUNT];
     float *out;                  // pitch-linear float4 image (may be peer memory), or nullptr when surf is used
     size_t pitch;                // bytes
+    float *mirror;               // optional second destination of every pixel store (pinned host memory mapped into the
+    size_t mirror_pitch;         // device address space: the device->host transfer fused into the kernel), or nullptr
     cudaSurfaceObject_t surf;    // external (Vulkan) image, when out == nullptr
     uint32_t *counters;          // 4 x uint32 per pixel or nullptr
     int W, H;

@@ -285,3 +285,20 @@ def test_bad_arguments_are_rejected_on_gpu(mm, assets):
     cs.dispatch()                                                     # still usable after the errors
     cs.synchronize()
     cs.close()
+
+
+def test_render_to_host_pinned_and_pageable_agree(mm, assets):
+    """mm_render_to_host fuses the device->host transfer into the kernel for page-locked destinations; the frame must be
+    bit-identical to the copy path (pageable destination) and to the device image."""
+    import torch
+    sc = scenes.make_scene(mm, "C1", assets, W=200, H=113)
+    cs = mm.ComputeShader(0, (200, 113), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+    cs.allocOutput()
+    pageable = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+    pinned_t = torch.full((113, 200, 4), -7.0, dtype=torch.float32).pin_memory()
+    pinned = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"], out=pinned_t.numpy())
+    device = cs.readOutput()
+    cs.close()
+    assert np.array_equal(pinned.view(np.uint32), pageable.view(np.uint32))
+    assert np.array_equal(pinned.view(np.uint32), device.view(np.uint32))
