@@ -103,6 +103,15 @@ MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
 MM_API int mm_synchronize(mm_ctx *ctx);
 
+/* ---- reprojection pass: replaces the ReprojectShader dispatch that precedes the cloud dispatch in the engine's
+ * frame (Shaders/reproject.comp; Shader.h:380-452; VulkanApplication.cpp:1053-1059).  Reads the PREVIOUS frame's
+ * image (descriptor set 1, backgroundTexturePrev) and writes the bound output image; needs camera and previous
+ * camera blocks from mm_set_uniforms.  A frame of the engine's cadence is
+ *     mm_set_uniforms; mm_dispatch_reproject; mm_dispatch(MM_PHASE16); swap the two images.
+ * (On one stream the two launches are ordered -- the reference records no barrier between them.) */
+MM_API int mm_bind_previous_linear(mm_ctx *ctx, const float *dptr_prev_rgba32f, size_t pitch_bytes);
+MM_API int mm_dispatch_reproject(mm_ctx *ctx, void *stream);
+
 /* host-buffer convenience (the end-to-end call): uniforms in, march, image out to HOST memory.
  * out_host: w*h*4 floats (packed).  Includes H2D of the uniforms and D2H of the image.  When out_host is
  * page-locked (cudaHostAlloc / cudaHostRegister) and mode is MM_FULL the D2H transfer is fused into the kernel

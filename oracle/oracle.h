@@ -34,6 +34,9 @@ float om_cloudLayerDensity(float relativeHeight, float cloudType);
 float om_heightBiasCoverage(float coverage, float height);
 int om_raySphereIntersection(const float ro[3], const float rd[3], const float sphere[4], float *t);
 
+/* reproject_oracle.c: restatement of reproject.comp:91-152 */
+int om_reproject(const void *camera160, const void *cameraPrev160, const float *src_rgba32f, int W, int H, float *dst_rgba32f);
+
 /* curl_noise_oracle.c: restatement of ImageUtils.cpp:25-223 */
 void om_generate_curl_noise(uint8_t *rgba8_128x128);
 float om_curl_hash(float x, float y, float z);           /* ImageUtils.cpp:25-29 */

@@ -64,6 +64,8 @@ def load_library():
         "mm_set_filter_mode": (i32, [vp, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
         "mm_synchronize": (i32, [vp]),
+        "mm_bind_previous_linear": (i32, [vp, vp, sz]),
+        "mm_dispatch_reproject": (i32, [vp, vp]),
         "mm_render_to_host": (i32, [vp, vp, vp, vp, i32, vp]),
         "mm_tonemap_rgba8": (i32, [vp, vp, i32, vp]),
         "mm_enable_counters": (i32, [vp, i32]),

@@ -36,8 +36,10 @@ struct mm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     TexSlot tex[TEX_COUNT];
-    float cam[40], sun[29], sky[13];
-    bool have_uniforms = false;
+    float cam[40], cam_prev[40], sun[29], sky[13];
+    bool have_uniforms = false, have_prev_camera = false;
+    const float *prev_image = nullptr;   // descriptor set 1 (resultImagePrev / sourceImage), caller-owned
+    size_t prev_pitch = 0;
     float *out = nullptr;          // bound output (may be external)
     float *own_out = nullptr;      // allocation owned by the context
     size_t pitch = 0;
@@ -252,7 +254,9 @@ int mm_build_noise_volumes(mm_ctx *ctx, uint64_t seed64, uint8_t *out_low, uint8
 int mm_set_uniforms(mm_ctx *ctx, const void *camera160, const void *camera_prev160, const void *sun116, const void *sky52) {
     if (!ctx) return MM_ERR_ARG;
     if (!camera160 || !sun116 || !sky52) return fail(ctx, MM_ERR_ARG, "mm_set_uniforms: null uniform block");
-    (void)camera_prev160;   // UniformCameraObjectPrev is declared but never read by the march (CC:19-23)
+    // UniformCameraObjectPrev is declared but never read by the march (CC:19-23); the reprojection pass reads it
+    ctx->have_prev_camera = camera_prev160 != nullptr;
+    if (camera_prev160) memcpy(ctx->cam_prev, camera_prev160, 160);
     memcpy(ctx->cam, camera160, 160);
     memcpy(ctx->sun, sun116, 116);
     memcpy(ctx->sky, sky52, 52);
@@ -408,6 +412,35 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     order_block_rows(p, p.block_row_order, nblockrows);
     CU(cudaEventRecord(ctx->ev0, stream));
     CU(launch_cloud_march(p, ctx->filter, stream));
+    CU(cudaEventRecord(ctx->ev1, stream));
+    ctx->timed = true;
+    return MM_OK;
+}
+
+int mm_bind_previous_linear(mm_ctx *ctx, const float *dptr, size_t pitch) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!dptr || (pitch & 15) || ((uintptr_t)dptr & 15)) return fail(ctx, MM_ERR_ARG, "mm_bind_previous_linear: need a 16-byte aligned pointer and pitch");
+    ctx->prev_image = dptr; ctx->prev_pitch = pitch;
+    return MM_OK;
+}
+
+int mm_dispatch_reproject(mm_ctx *ctx, void *stream_v) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!ctx->have_uniforms || !ctx->have_prev_camera) return fail(ctx, MM_ERR_STATE, "mm_dispatch_reproject: camera and previous camera blocks are required");
+    if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_dispatch_reproject: no linear output image bound");
+    if (!ctx->prev_image) return fail(ctx, MM_ERR_STATE, "mm_dispatch_reproject: no previous image bound (mm_bind_previous_linear)");
+    if (ctx->prev_image == ctx->out) return fail(ctx, MM_ERR_ARG, "mm_dispatch_reproject: previous and target image must differ (ping-pong)");
+    if (ctx->prev_pitch < (size_t)ctx->W * 16) return fail(ctx, MM_ERR_ARG, "mm_dispatch_reproject: previous image pitch < 16*w");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    ReprojectParams p;
+    memcpy(p.cam, ctx->cam, 160);
+    memcpy(p.cam_prev, ctx->cam_prev, 160);
+    p.src = ctx->prev_image; p.src_pitch = ctx->prev_pitch;
+    p.dst = ctx->out; p.dst_pitch = ctx->pitch;
+    p.W = ctx->W; p.H = ctx->H;
+    CU(cudaEventRecord(ctx->ev0, stream));
+    CU(launch_reproject(p, stream));
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->timed = true;
     return MM_OK;

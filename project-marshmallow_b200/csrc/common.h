@@ -47,6 +47,13 @@ struct MarchParams {
     uint16_t block_row_order[1024];
 };
 
+struct ReprojectParams {
+    float cam[40], cam_prev[40];     // UniformCameraObject, UniformCameraObjectPrev (reproject.comp:12-23)
+    const float *src; size_t src_pitch;   // sourceImage (previous frame), pitch-linear float4
+    float *dst; size_t dst_pitch;         // targetImage
+    int W, H;
+};
+cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
 cudaError_t launch_det_pow(const float *x, const float *y, int n, float *out, cudaStream_t stream);

@@ -151,6 +151,14 @@ class ComputeShader:
         sp = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
         self._check(self._lib.mm_dispatch(self._ctx, mode, row_begin, row_stride, row_block, sp))
 
+    def bindPrevious(self, device_ptr, pitch_bytes=None):
+        """descriptor set 1 (backgroundTexturePrev): the previous frame's image, read by the reprojection pass"""
+        self._check(self._lib.mm_bind_previous_linear(self._ctx, C.c_void_p(int(device_ptr)), pitch_bytes or self.width * 16))
+
+    def dispatchReproject(self, stream=None):
+        sp = None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+        self._check(self._lib.mm_dispatch_reproject(self._ctx, sp))
+
     def synchronize(self):
         self._check(self._lib.mm_synchronize(self._ctx))
 

@@ -39,6 +39,7 @@ def lib():
             fn.restype, fn.argtypes = f32, [f32] * n
         l.om_curl_hash_index.restype, l.om_curl_hash_index.argtypes = i32, [f32] * 3
         l.om_raySphereIntersection.argtypes = [vp, vp, vp, vp]
+        l.om_reproject.argtypes = [vp, vp, vp, i32, i32, vp]
         l.om_generate_curl_noise.argtypes = [vp]
         l.om_build_noise_volumes.argtypes = [C.c_uint64, vp, vp]
         l.om_noise_hash.restype, l.om_noise_hash.argtypes = C.c_uint32, [C.c_uint32] * 4
@@ -106,6 +107,15 @@ def tonemap_rgba8(img):
     out = np.empty(img.shape, np.uint8)
     lib().om_tonemap_rgba8(_p(img), img.size // 4, _p(out))
     return out
+
+
+def reproject(cam, cam_prev, src):
+    cam, cam_prev = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(cam_prev, np.float32)
+    src = np.ascontiguousarray(src, np.float32)
+    H, W, _ = src.shape
+    dst = np.empty_like(src)
+    assert lib().om_reproject(_p(cam), _p(cam_prev), _p(src), W, H, _p(dst)) == 0
+    return dst
 
 
 def generate_curl_noise():
