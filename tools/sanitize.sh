@@ -1,0 +1,34 @@
+#!/bin/bash
+# compute-sanitizer pass over the kernels (run on the GPU box): memcheck + racecheck on a small frame of every mode,
+# the noise builds, the reprojection pass and the tonemap.  Output -> gpurun_out/sanitizer_*.log
+mkdir -p gpurun_out
+cat > /tmp/san_driver.py <<'PY'
+import sys, os
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, _pkg, scenes
+mm = _pkg.load_package()
+assets = scenes.load_assets()
+W, H = 96, 54
+sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"], lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+cs.allocOutput()
+for counters in (False, True):
+    cs.enableCounters(counters)
+    for mode in (mm.MM_FILTER_EXACT, mm.MM_FILTER_HW, mm.MM_FILTER_HYBRID):
+        cs.setFilterMode(mode)
+        cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+        cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sc["sun"])
+        cs.dispatch(mm.MM_PHASE16)
+        cs.dispatch(mm.MM_FULL, 1, 3, 2)
+        cs.synchronize()
+cs.tonemapRGBA8()
+cs.buildCurlNoise()
+if "--volumes" in sys.argv:
+    cs.buildNoiseVolumes(1)
+cs.close()
+print("sanitizer driver done")
+PY
+for tool in memcheck racecheck; do
+  compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_driver.py > gpurun_out/sanitizer_$tool.log 2>&1
+  echo "$tool exit=$?"; tail -4 gpurun_out/sanitizer_$tool.log
+done
