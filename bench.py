@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--filter", default="hybrid", choices=["exact", "hw", "hybrid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--row-block", type=int, default=4)
+    ap.add_argument("--animation", type=int, default=0, help="frame-parallel wind animation of N frames (BASELINE config 5): frame k on rank k %% world")
     return ap.parse_args()
 
 
@@ -138,6 +139,60 @@ def run_reference(args):
     }))
 
 
+def run_animation(args, mm, cs, sc, multigpu, dist, rank, world, local):
+    """BASELINE config 5 as a job: N whole frames of a wind animation (sky.wind.w = 8*k), frame k rendered by
+    rank k % world into its slot of rank 0's frame ring over NVLink.  One step = the whole animation."""
+    import torch
+    W, H, F = sc["W"], sc["H"], args.animation
+    ring = multigpu.FrameRing(cs, rank, world, dist if world > 1 else None)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    mine = ring.frames_of(F)
+    sky = sc["sky"].copy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def job():
+        for k in mine:
+            sky[11] = 8.0 * k
+            cs.updateUniformBuffers(sc["cam"], None, sky, sc["sun"])
+            cs.dispatch(mm.MM_FULL, stream=stream.cuda_stream)
+
+    for _ in range(max(1, args.warmup // 3)):
+        job()
+    barrier()
+    times = []
+    for _ in range(max(1, args.steps // 10)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        job()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t))
+    ms = sum(times) / len(times)
+    if rank == 0:
+        print(json.dumps({"metric": "cloud-march throughput", "value": F * W * H / ms / 1e3, "unit": "Mpix/s", "n_gpus": world, "steps": len(times),
+                          "warmup": max(1, args.warmup // 3), "ms_per_step": ms, "ms_per_frame": ms / F, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gpu_launches": len(times) * len(mine),
+                          "config": {"workload": f"{args.config} {W}x{H} x {F}-frame wind animation (sky.wind.w = 8k), frame-parallel: frame k on rank k % {world}",
+                                     "filter": args.filter, "l2": "frames are 531 MB at 8K (> L2); no flush", "parallelism": f"frame-parallel x{world}, frames stored into rank 0's ring over NVLink"}}))
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+    ring.close()
+    cs.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -168,8 +223,10 @@ def main():
     cs.setFilterMode(fmode)
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
 
-    # output image lives on rank 0; other ranks map it through CUDA IPC and store into it over NVLink
     from project_marshmallow_b200 import multigpu
+    if args.animation > 0:
+        return run_animation(args, mm, cs, sc, multigpu, dist, rank, world, local)
+    # output image lives on rank 0; other ranks map it through CUDA IPC and store into it over NVLink
     shared = multigpu.SharedFrame(cs, rank, world, dist if world > 1 else None)
 
     stream = torch.cuda.Stream()            # every launch and every event of the timed region is on this stream
@@ -272,6 +329,13 @@ def main():
             # exact command come from the committed ncu capture (profiles/); peak = 148 SM x 4 schedulers x f_SM.
             prof = os.path.join(ROOT, "profiles", f"r01_final_{args.filter}.summary.csv")
             if os.path.exists(prof) and args.config == "C2" and world == 1:
+                rows = {l.split(",")[0]: l.strip().split(",") for l in open(prof) if l.count(",") >= 2}
+                unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                try:        # DRAM bytes of one launch of this command, from the committed ncu --set full capture
+                    out["roofline"]["traffic"] = sum(float(rows[k][2]) * unit[rows[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                    out["roofline"]["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, " + os.path.relpath(prof, ROOT) + "); the 33 MB image mostly stays in L2 at kernel end"
+                except (KeyError, ValueError):
+                    pass
                 winst = [float(l.split(",")[2]) for l in open(prof) if l.startswith("smsp__inst_executed.sum,")]
                 if winst:
                     peak_issue = N_SM * 4 * peaks["sm_max_mhz"] * 1e6

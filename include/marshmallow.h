@@ -144,7 +144,10 @@ MM_API int mm_selftest_div(mm_ctx *ctx, int which, float *constant_out, unsigned
  * One process per GPU.  Rank 0 exports the allocation behind its output image as a 64-byte CUDA-IPC
  * handle; the other ranks open it and bind the mapped pointer with mm_bind_output_linear, so their
  * march kernels store finished pixels straight into rank 0's image over NVLink (no gather step).
- * dptr must be the base of an allocation made by mm_alloc_output. */
+ * dptr must be the base of an allocation made by mm_alloc_output or mm_alloc_device.  For frame-parallel animation
+ * (BASELINE config 5) rank 0 allocates one slot per rank with mm_alloc_device and every rank binds its own slot. */
+MM_API int mm_alloc_device(mm_ctx *ctx, size_t bytes, void **dptr_out);    /* plain device allocation (IPC-exportable base) */
+MM_API int mm_free_device(mm_ctx *ctx, void *dptr);
 MM_API int mm_ipc_get_handle(mm_ctx *ctx, void *dptr, uint8_t handle_out[64]);
 MM_API int mm_ipc_open_handle(mm_ctx *ctx, const uint8_t handle[64], void **dptr_out);
 MM_API int mm_ipc_close_handle(mm_ctx *ctx, void *dptr);

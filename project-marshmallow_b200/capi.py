@@ -75,6 +75,8 @@ def load_library():
         "mm_sample": (i32, [vp, i32, i32, vp, i32, vp]),
         "mm_det_pow": (i32, [vp, vp, vp, i32, vp]),
         "mm_selftest_div": (i32, [vp, i32, fp, C.POINTER(C.c_uint64)]),
+        "mm_alloc_device": (i32, [vp, sz, C.POINTER(vp)]),
+        "mm_free_device": (i32, [vp, vp]),
         "mm_ipc_get_handle": (i32, [vp, vp, vp]),
         "mm_ipc_open_handle": (i32, [vp, vp, C.POINTER(vp)]),
         "mm_ipc_close_handle": (i32, [vp, vp]),

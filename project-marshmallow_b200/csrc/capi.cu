@@ -567,6 +567,20 @@ int mm_selftest_div(mm_ctx *ctx, int which, float *constant_out, unsigned long l
     return MM_OK;
 }
 
+int mm_alloc_device(mm_ctx *ctx, size_t bytes, void **dptr_out) {
+    if (!ctx || !dptr_out || bytes == 0) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMalloc(dptr_out, bytes));
+    return MM_OK;
+}
+
+int mm_free_device(mm_ctx *ctx, void *dptr) {
+    if (!ctx || !dptr) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaFree(dptr));
+    return MM_OK;
+}
+
 int mm_ipc_get_handle(mm_ctx *ctx, void *dptr, uint8_t handle_out[64]) {
     if (!ctx || !dptr || !handle_out) return MM_ERR_ARG;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");

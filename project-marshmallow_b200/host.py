@@ -121,6 +121,14 @@ class ComputeShader:
         self.out_ptr, self.out_pitch = int(device_ptr), pitch
 
     # ---- multi-GPU: CUDA-IPC export / import of the output image
+    def allocDevice(self, nbytes):
+        p = C.c_void_p()
+        self._check(self._lib.mm_alloc_device(self._ctx, nbytes, C.byref(p)))
+        return p.value
+
+    def freeDevice(self, device_ptr):
+        self._check(self._lib.mm_free_device(self._ctx, C.c_void_p(int(device_ptr))))
+
     def ipcGetHandle(self, device_ptr):
         h = np.zeros(64, np.uint8)
         self._check(self._lib.mm_ipc_get_handle(self._ctx, C.c_void_p(int(device_ptr)), _ptr(h)))

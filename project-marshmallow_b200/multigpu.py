@@ -56,3 +56,35 @@ class SharedFrame:
         if self.remote_ptr is not None:
             self.cs.ipcCloseHandle(self.remote_ptr)
             self.remote_ptr = None
+
+
+class FrameRing:
+    """Frame-parallel animation (BASELINE config 5): frame k is rendered whole by rank k % world.  Rank 0 owns one
+    image slot per rank; every rank binds ITS slot (mapped through CUDA IPC on ranks != 0) and stores finished frames
+    there over NVLink, so rank 0 always holds the latest frame of every rank without a gather step."""
+
+    def __init__(self, cs, rank, world, dist=None):
+        self.cs, self.rank, self.world = cs, rank, world
+        self.frame_bytes = cs.width * cs.height * 16
+        self.base = self.remote = None
+        handle = None
+        if rank == 0:
+            self.base = cs.allocDevice(self.frame_bytes * world)
+            if world > 1:
+                handle = cs.ipcGetHandle(self.base)
+        handle = exchange_handle(handle, rank, world, dist)
+        if rank != 0:
+            self.remote = cs.ipcOpenHandle(handle)
+        self.slot = (self.base if rank == 0 else self.remote) + rank * self.frame_bytes
+        cs.bindOutput(self.slot, cs.width * 16)
+
+    def frames_of(self, n_frames):
+        return list(range(self.rank, n_frames, self.world))
+
+    def close(self):
+        if self.remote is not None:
+            self.cs.ipcCloseHandle(self.remote)
+            self.remote = None
+        if self.base is not None:
+            self.cs.freeDevice(self.base)
+            self.base = None
