@@ -351,9 +351,9 @@ static void light_cone_samples(const float *sun, float out[18]) {
 static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows) {
     const float *cam = p.cam;
     struct Key { float k; uint16_t i; };
-    static thread_local Key keys[1024];
+    static thread_local Key keys[4096];
     for (int b = 0; b < nblockrows; b++) {
-        int j = b * 8 + 4, py;
+        int j = b * BLOCK_H + BLOCK_H / 2, py;
         if (p.mode == DISPATCH_PHASE16) py = j * 4;
         else { int k = j / p.row_block; py = (p.row_begin + k * p.row_stride) * p.row_block + (j - k * p.row_block); }
         if (py >= p.H) py = p.H - 1;
@@ -407,8 +407,8 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         p.owned_rows = (ctx->H + 3) / 4;
         p.grid_w = (ctx->W + 3) / 4;
     }
-    int nblockrows = (p.owned_rows + 7) / 8;
-    if (nblockrows > 1024) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: more than 8192 rows per dispatch");
+    int nblockrows = (p.owned_rows + BLOCK_H - 1) / BLOCK_H;
+    if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
     order_block_rows(p, p.block_row_order, nblockrows);
     CU(cudaEventRecord(ctx->ev0, stream));
     CU(launch_cloud_march(p, ctx->filter, stream));

@@ -22,6 +22,12 @@ enum { TEX_PLACEMENT = 0, TEX_NIGHTSKY = 1, TEX_CURL = 2, TEX_LOWRES = 3, TEX_HI
 enum { FILTER_EXACT = 0, FILTER_HW = 1, FILTER_HYBRID = 2 };
 enum { DISPATCH_FULL = 0, DISPATCH_PHASE16 = 1 };
 
+// Pixel tile of one warp: MM_TILE_W x (32 / MM_TILE_W); a block is 2 x 2 warps.
+#ifndef MM_TILE_W
+#define MM_TILE_W 8
+#endif
+enum { TILE_W = MM_TILE_W, TILE_H = 32 / MM_TILE_W, BLOCK_W = 2 * TILE_W, BLOCK_H = 2 * TILE_H };
+
 struct MarchParams {
     float cam[40];   // UniformCameraObject (Shader.h:24-29)
     float sun[29];   // UniformSunObject    (SkyManager.h:8-14)
@@ -40,11 +46,11 @@ struct MarchParams {
     int row_begin, row_stride, row_block;
     int owned_rows;              // rows this dispatch enumerates (FULL), virtual rows (PHASE16)
     int grid_w;                  // pixel columns enumerated (W, or ceil(W/4) in PHASE16)
-    // Execution order of the 8-row block rows, most expensive first (rays nearest the horizon cross the longest
+    // Execution order of the BLOCK_H-row block rows, most expensive first (rays nearest the horizon cross the longest
     // stretch of the cloud shell; rays below it are free): blockIdx.y -> block row.  Keeps the tail of the launch
     // cheap, which is what limits strong scaling when a GPU owns only a few waves of tiles.  Built on the host
     // per dispatch (capi.cu, order_block_rows); affects scheduling only, never results.
-    uint16_t block_row_order[1024];
+    uint16_t block_row_order[4096];
 };
 
 struct ReprojectParams {
