@@ -211,6 +211,12 @@ def test_full_size_baseline_configs_pass_the_parity_gate(mm, oracle, assets, nam
     assert rep["branch_flip_pixels"] == 0
     assert rep["alpha_identical_frac"] == 1.0
     assert rep["max_abs_diff_8bit"] <= 2 and rep["frac_within_1"] >= 0.999
+    # the production variant (no fetch counters; in HYBRID its light-cone samples use the relaxed arithmetic path)
+    img2, _ = _render(mm, sc, mm.MM_FILTER_EXACT if mode == "exact" else mm.MM_FILTER_HYBRID, counters=False)
+    rep2 = oracle.parity_report(ref, img2)
+    print(name, mode, "production variant", rep2)
+    assert rep2["alpha_identical_frac"] == 1.0            # alpha = f(accumulated density): every decision still exact
+    assert rep2["max_abs_diff_8bit"] <= 2 and rep2["frac_within_1"] >= 0.999
 
 
 def test_size_independent_properties_at_8k(mm, assets):
