@@ -195,7 +195,7 @@ def test_exact_divide_by_constant_is_the_ieee_quotient(mm):
         assert bad == 0, f"div_const(x, {c!r}) differs from x / {c!r} for {bad} dividends"
         which += 1
     cs.close()
-    assert len(seen) >= 10
+    assert len(seen) >= 13          # 10 constants + sqrt + rcp + remapClampedTo1
 
 
 @pytest.mark.parametrize("name,mode", [("C2", "hybrid"), ("C2", "exact"), ("C3", "hybrid")])
