@@ -2,7 +2,7 @@
 //
 // What the reference does with Vulkan objects in ComputeShader (Shader.h:286-377, Shader.cpp:633-992)
 // and Texture/Texture3D (Texture.cpp) is done here with CUDA objects:
-//   descriptor set 2 samplers  -> per-slot {uchar4 cudaArray + texture object, float4 linear copy}
+//   descriptor set 2 samplers  -> per-slot {uchar4 cudaArray + texture object, pair-major float copy (cloud_march.cu)}
 //   4 uniform buffers + memcpy -> MarchParams passed by value as a __grid_constant__ kernel argument
 //   descriptor set 0 image     -> pitch-linear float4 pointer (own, caller's or a peer GPU's) or a
 //                                 surface object over imported Vulkan memory
@@ -15,6 +15,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "../../include/marshmallow.h"
@@ -226,7 +227,8 @@ int mm_build_curl_noise(mm_ctx *ctx, uint8_t *out_host) {
     if (!ctx->scratch) CU(cudaMalloc(&ctx->scratch, (15 * N + 8) * sizeof(float) + TBL));
     unsigned char *dtable = reinterpret_cast<unsigned char *>(ctx->scratch + 15 * N + 8);
     static unsigned char htable[26 * 26 * 26];
-    build_curl_gradient_table(htable);
+    static std::once_flag htable_once;
+    std::call_once(htable_once, build_curl_gradient_table, htable);
     CU(cudaMemcpyAsync(dtable, htable, TBL, cudaMemcpyHostToDevice, ctx->stream));
     int rc = ensure_stage(ctx, N * 4);
     if (rc) return rc;
