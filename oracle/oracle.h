@@ -8,7 +8,7 @@ extern "C" {
 #endif
 
 enum { OM_TEX_PLACEMENT = 0, OM_TEX_NIGHTSKY = 1, OM_TEX_CURL = 2, OM_TEX_LOWRES = 3, OM_TEX_HIRES = 4 };
-enum { OM_FILTER_FP32 = 0, OM_FILTER_FIX8 = 1 };
+enum { OM_FILTER_FP32 = 0, OM_FILTER_FIX8 = 1, OM_FILTER_TEXUNIT = 2 /* bit-exact model of the B200 texture unit */ };
 enum { OM_POW_DET = 0, OM_POW_LIBM = 1 };
 enum { OM_FULL = 0, OM_PHASE16 = 1 };
 

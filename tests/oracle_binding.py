@@ -13,7 +13,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_CURL_SO = os.path.join(ROOT, "oracle", "_ref", "libref_curl.so")
 
 OM_TEX_PLACEMENT, OM_TEX_NIGHTSKY, OM_TEX_CURL, OM_TEX_LOWRES, OM_TEX_HIRES = range(5)
-OM_FILTER_FP32, OM_FILTER_FIX8 = 0, 1
+OM_FILTER_FP32, OM_FILTER_FIX8, OM_FILTER_TEXUNIT = 0, 1, 2
 OM_POW_DET, OM_POW_LIBM = 0, 1
 OM_FULL, OM_PHASE16 = 0, 1
 

@@ -65,14 +65,58 @@ def test_hybrid_mode_decisions_match_oracle(mm, oracle, assets):
     assert rep["pass"], rep
 
 
-def test_hw_mode_against_fix8_oracle_reports_tail(mm, oracle, assets):
-    """FILTER_HW is the speed grade: compared with the oracle's 8-bit-weight sampler.  The march is chaotic
-    at its thresholds, so a tail of flipped pixels is expected (hard part 2); it is bounded here."""
-    sc = scenes.make_scene(mm, "C1", assets, W=320, H=180)
-    ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle.OM_FILTER_FIX8).march(320, 180)
+def test_hw_sampler_is_the_texunit_model(mm, oracle, assets):
+    """The live texture unit against the oracle's integer model of it (OM_FILTER_TEXUNIT): bit-identical on fresh
+    random coordinates for the four march textures and for a non-power-of-two 2D texture (star-map-like)."""
+    rng = np.random.default_rng(41)
+    star = rng.integers(0, 256, (27, 50, 4), dtype=np.uint8)
+    tex = {"placement": assets["placement"], "curl": assets["curl"], "lowres": assets["lowres"], "hires": assets["hires"]}
+    S = oracle.Scene(tex, np.zeros(40, np.float32), np.zeros(29, np.float32), np.zeros(13, np.float32), nightsky=star)
+    cs = mm.ComputeShader(0, (8, 8), placement=tex["placement"], curl=tex["curl"], lowRes=tex["lowres"], hiRes=tex["hires"], nightSky=star)
+    for slot, lo, hi in ((mm.MM_TEX_PLACEMENT, -2, 2), (mm.MM_TEX_CURL, -20, 20), (mm.MM_TEX_LOWRES, -4, 4), (mm.MM_TEX_HIRES, -80, 80)):
+        uvw = rng.uniform(lo, hi, (200000, 3)).astype(np.float32)
+        uvw[:64] = np.float32([[i / 128.0, i / 64.0 - 0.25, 1.0 - i / 32.0] for i in range(64)])   # texel centres / edges
+        got = cs.sample(slot, mm.MM_FILTER_HW, uvw)
+        want = S.sample(slot, oracle.OM_FILTER_TEXUNIT, uvw)
+        bad = (got.view(np.uint32) != want.view(np.uint32)).any(axis=1)
+        assert not bad.any(), (slot, int(bad.sum()), uvw[bad][:4], got[bad][:4], want[bad][:4])
+    cs.close()
+
+
+@pytest.mark.parametrize("name,W,H", [("C1", 320, 180), ("C3", 320, 180), ("C2b", 256, 144), ("C5", 256, 144), ("C5b", 256, 144)])
+def test_hw_mode_matches_texunit_oracle(mm, oracle, assets, name, W, H):
+    """FILTER_HW marches with the hardware sampler.  Against the oracle filtering with the bit-exact model of that
+    sampler -- the reference shader as it runs on this GPU -- every decision is identical: zero branch flips,
+    identical fetch counters, bit-identical alpha; RGB differs only through the shading transcendentals."""
+    sc = scenes.make_scene(mm, name, assets, W=W, H=H)
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle.OM_FILTER_TEXUNIT)
+    ref, rcnt = S.march(W, H)
     img, cnt = _render(mm, sc, mm.MM_FILTER_HW)
     rep = oracle.parity_report(ref, img, rcnt, cnt)
-    print("hw vs fix8", rep)
+    print(name, "hw vs texunit oracle", rep)
+    assert rep["branch_flip_pixels"] == 0
+    assert rep["counter_mismatch_pixels"] == 0
+    assert rep["alpha_identical_frac"] == 1.0
+    assert rep["max_abs_diff_8bit"] <= 1 and rep["frac_within_1"] == 1.0
+    rel = np.abs(ref - img) / np.maximum(np.abs(ref), 1e-6)
+    assert rel.max() < 1e-4
+    # production variant (no counters): light-cone samples take the relaxed-arithmetic path
+    img2, _ = _render(mm, sc, mm.MM_FILTER_HW, counters=False)
+    rep2 = oracle.parity_report(ref, img2)
+    print(name, "hw production variant", rep2)
+    assert rep2["alpha_identical_frac"] == 1.0
+    assert rep2["max_abs_diff_8bit"] <= 2 and rep2["frac_within_1"] >= 0.999
+
+
+def test_hw_mode_against_float_filter_oracle_reports_tail(mm, oracle, assets):
+    """The same frame under the two sampler definitions (hardware 8-bit weights vs exact binary32 weights) differs
+    by a tail of pixels whose rays flip a threshold (the march is chaotic there, SURVEY 7 hard part 2): two
+    conformant Vulkan implementations differ the same way.  Reported and bounded, not hidden."""
+    sc = scenes.make_scene(mm, "C1", assets, W=320, H=180)
+    ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"]).march(320, 180)
+    img, cnt = _render(mm, sc, mm.MM_FILTER_HW)
+    rep = oracle.parity_report(ref, img, rcnt, cnt)
+    print("hw vs float-filter oracle", rep)
     assert rep["frac_within_1"] > 0.97
     assert rep["branch_flip_pixels"] < 0.05 * 320 * 180
 
@@ -198,21 +242,25 @@ def test_exact_divide_by_constant_is_the_ieee_quotient(mm):
     assert len(seen) >= 13          # 10 constants + sqrt + rcp + remapClampedTo1
 
 
-@pytest.mark.parametrize("name,mode", [("C2", "hybrid"), ("C2", "exact"), ("C3", "hybrid")])
+_FILTERS = {"exact": ("MM_FILTER_EXACT", "OM_FILTER_FP32"), "hybrid": ("MM_FILTER_HYBRID", "OM_FILTER_FP32"), "hw": ("MM_FILTER_HW", "OM_FILTER_TEXUNIT")}
+
+
+@pytest.mark.parametrize("name,mode", [("C2", "hw"), ("C3", "hw"), ("C2", "hybrid"), ("C2", "exact"), ("C3", "hybrid")])
 def test_full_size_baseline_configs_pass_the_parity_gate(mm, oracle, assets, name, mode):
     """BASELINE configs at their FULL size (1920x1080 noon, 3840x2160 sunset): the north-star gate -- max <= 2/255
     per channel, >= 99.9 % of pixels within 1/255 after the reference tonemap -- plus zero branch flips."""
     sc = scenes.make_scene(mm, name, assets)
     W, H = sc["W"], sc["H"]
-    ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"]).march(W, H)
-    img, cnt = _render(mm, sc, mm.MM_FILTER_EXACT if mode == "exact" else mm.MM_FILTER_HYBRID)
+    kfilter, ofilter = getattr(mm, _FILTERS[mode][0]), getattr(oracle, _FILTERS[mode][1])
+    ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=ofilter).march(W, H)
+    img, cnt = _render(mm, sc, kfilter)
     rep = oracle.parity_report(ref, img, rcnt, cnt)
     print(name, mode, rep)
     assert rep["branch_flip_pixels"] == 0
     assert rep["alpha_identical_frac"] == 1.0
     assert rep["max_abs_diff_8bit"] <= 2 and rep["frac_within_1"] >= 0.999
     # the production variant (no fetch counters; in HYBRID its light-cone samples use the relaxed arithmetic path)
-    img2, _ = _render(mm, sc, mm.MM_FILTER_EXACT if mode == "exact" else mm.MM_FILTER_HYBRID, counters=False)
+    img2, _ = _render(mm, sc, kfilter, counters=False)
     rep2 = oracle.parity_report(ref, img2)
     print(name, mode, "production variant", rep2)
     assert rep2["alpha_identical_frac"] == 1.0            # alpha = f(accumulated density): every decision still exact

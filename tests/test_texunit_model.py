@@ -1,0 +1,77 @@
+"""The oracle's OM_FILTER_TEXUNIT sampler (oracle/cloud_march_oracle.c: texunit_sample) against outputs RECORDED FROM THE
+B200 TEXTURE UNIT (tests/golden/texunit_probe.npz; recorded by tools/texprobe.py on the GPU box, condensed by
+tools/make_texunit_golden.py).  Bar: bit-identical on every recorded sample.  The -m gpu half replays fresh random
+coordinates against the live hardware (tests/test_march_parity_gpu.py::test_hw_sampler_is_the_texunit_model)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "texunit_probe.npz")
+
+
+class _OneTex:
+    """An oracle scene holding one texture in a chosen slot (the sampler only needs the texels)."""
+    def __init__(self, oracle, tex, slot):
+        self.o, self.slot = oracle, slot
+        self.s = oracle.lib().om_scene_create()
+        a = np.ascontiguousarray(tex, np.uint8)
+        d, h, w = (1,) + a.shape[:2] if a.ndim == 3 else a.shape[:3]
+        assert oracle.lib().om_scene_set_texture(self.s, slot, a.ctypes.data, w, h, d) == 0
+
+    def sample(self, uvw):
+        uvw = np.ascontiguousarray(uvw, np.float32)
+        out = np.empty((len(uvw), 4), np.float32)
+        assert self.o.lib().om_sample(self.s, self.slot, self.o.OM_FILTER_TEXUNIT, uvw.ctypes.data, len(uvw), out.ctypes.data) == 0
+        return out
+
+    def close(self):
+        self.o.lib().om_scene_destroy(self.s)
+
+
+def _check(got, x16, name):
+    want = (x16.astype(np.float64) / 65535.0).astype(np.float32)
+    bad = (got.view(np.uint32) != want.view(np.uint32)).any(axis=1)
+    assert not bad.any(), f"{name}: {int(bad.sum())} of {len(bad)} samples differ from the hardware recording"
+
+
+@pytest.mark.parametrize("group,names,is3d", [
+    ("ramp4", ("ramp4", "ramp4_shift0", "ramp4_shift1", "ramp4_shift2", "ramp4_shift3"), False),
+    ("npot5", ("npot5",), False),
+    ("quad2x2_grid", ("quad2x2_grid", "quad2x2_rand"), False),
+    ("cube2_grid", ("cube2_grid", "cube2_rand"), True),
+    ("cube4_rand", ("cube4_rand",), True),
+])
+def test_synthetic_texels_match_the_hardware_recording(oracle, group, names, is3d):
+    g = np.load(GOLD)
+    t = _OneTex(oracle, g[group + "_tex"], oracle.OM_TEX_LOWRES if is3d else oracle.OM_TEX_PLACEMENT)
+    for n in names:
+        _check(t.sample(g[n + "_uvw"]), g[n + "_x16"], n)
+    t.close()
+
+
+def test_shipped_textures_match_the_hardware_recording(oracle, assets):
+    g = np.load(GOLD)
+    for name, slot in (("placement", oracle.OM_TEX_PLACEMENT), ("curl", oracle.OM_TEX_CURL),
+                       ("lowres", oracle.OM_TEX_LOWRES), ("hires", oracle.OM_TEX_HIRES)):
+        t = _OneTex(oracle, assets[name], slot)
+        _check(t.sample(g[f"asset_{name}_uvw"]), g[f"asset_{name}_x16"], name)
+        t.close()
+
+
+def test_texunit_weights_partition_unity_and_constants_are_fixed_points(oracle):
+    """Model properties: a constant texture filters to exactly its UNORM value at any coordinate (the corner weights
+    sum to 256), and texel centres return the texel."""
+    rng = np.random.default_rng(2)
+    for v in (0, 1, 37, 128, 254, 255):
+        t = _OneTex(oracle, np.full((4, 4, 4, 4), v, np.uint8), oracle.OM_TEX_LOWRES)
+        out = t.sample(rng.uniform(-5, 5, (5000, 3)).astype(np.float32))
+        t.close()
+        assert np.array_equal(out, np.full_like(out, np.float32(v * 257 / 65535.0)))
+    tex = rng.integers(0, 256, (4, 8, 16, 4), dtype=np.uint8)
+    t = _OneTex(oracle, tex, oracle.OM_TEX_LOWRES)
+    z, y, x = np.meshgrid(np.arange(4), np.arange(8), np.arange(16), indexing="ij")
+    uvw = np.stack([(x.ravel() + 0.5) / 16, (y.ravel() + 0.5) / 8, (z.ravel() + 0.5) / 4], 1).astype(np.float32)
+    out = t.sample(uvw)
+    t.close()
+    assert np.array_equal(out, (tex.reshape(-1, 4).astype(np.float64) * 257 / 65535.0).astype(np.float32))

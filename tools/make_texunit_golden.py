@@ -1,0 +1,37 @@
+"""Condense the hardware probe recordings (gpurun_out/texprobe.npz, written ON A B200 by tools/texprobe.py) into the
+committed fixture tests/golden/texunit_probe.npz: coordinates and the texture unit's recorded outputs (as the 16-bit
+UNORM integers they are) for synthetic texels and for the four shipped march textures.  The fixture pins the oracle's
+OM_FILTER_TEXUNIT sampler model on the CPU; tests/test_texunit_model.py replays it."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+d = np.load(os.path.join(ROOT, "gpurun_out", "texprobe.npz"))
+rng = np.random.default_rng(11)
+out = {}
+
+def put(name, tex, uvw, res, n):
+    idx = np.sort(rng.choice(len(uvw), size=min(n, len(uvw)), replace=False))
+    x16 = np.round(res[idx].astype(np.float64) * 65535.0)
+    assert np.array_equal((x16 / 65535.0).astype(np.float32), res[idx]), name       # outputs are exactly X/65535
+    out[name + "_uvw"] = uvw[idx].astype(np.float32)
+    out[name + "_x16"] = x16.astype(np.uint16)
+    if tex is not None:
+        out[name + "_tex"] = tex
+
+def sweep(u):
+    return np.stack([u, np.full(len(u), 0.5, np.float32), np.zeros(len(u), np.float32)], 1)
+
+put("ramp4", d["A_tex"], sweep(d["A_u"]), d["A_out"], 8000)
+for k in range(4):
+    put(f"ramp4_shift{k}", None, sweep(d[f"A_shift{k}_u"]), d[f"A_shift{k}_out"], 3000)
+put("npot5", d["B_tex"], sweep(d["B_u"]), d["B_out"], 8000)
+put("quad2x2_grid", d["C_tex"], d["C_uv"], d["C_out"], 8000)
+put("quad2x2_rand", None, d["C_ruv"], d["C_rout"], 8000)
+put("cube2_grid", d["D_tex"], d["D_uvw"], d["D_out"], 12000)
+put("cube2_rand", None, d["D_ruvw"], d["D_rout"], 12000)
+put("cube4_rand", d["E_tex"], d["E_ruvw"], d["E_rout"], 12000)
+for name in ("placement", "curl", "lowres", "hires"):          # texels: tests/golden/assets
+    put("asset_" + name, None, d[f"F_{name}_uvw"], d[f"F_{name}_out"], 12000)
+path = os.path.join(ROOT, "tests", "golden", "texunit_probe.npz")
+np.savez_compressed(path, **out)
+print(path, os.path.getsize(path), "bytes")
