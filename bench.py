@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
-    ap.add_argument("--filter", default="hybrid", choices=["exact", "hw", "hybrid"])
+    ap.add_argument("--filter", default="hw", choices=["exact", "hw", "hybrid"],
+                    help="hw (default): texture-unit filtering, parity against the oracle's bit-exact texture-unit model; "
+                         "exact / hybrid: FP32 software filtering of the march samples, parity against the oracle's binary32 sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--row-block", type=int, default=4)
     ap.add_argument("--animation", type=int, default=0, help="frame-parallel wind animation of N frames (BASELINE config 5): frame k on rank k %% world")
@@ -88,10 +90,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
-def workload_Q(oracle_binding, sc, rows_step):
+def oracle_filter(ob, kernel_filter):
+    """The oracle sampler that defines parity for a kernel filter mode."""
+    return ob.OM_FILTER_TEXUNIT if kernel_filter == "hw" else ob.OM_FILTER_FP32
+
+
+def workload_Q(oracle_binding, sc, rows_step, kernel_filter):
     """Algorithmic work per pixel: Q = N2D + 2*N3D bilinear-quad ops, from the oracle's counters on
     a row subsample of the same frame (every rows_step-th row)."""
-    S = oracle_binding.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    S = oracle_binding.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(oracle_binding, kernel_filter))
     t0 = time.time()
     _, cnt = S.march(sc["W"], sc["H"], row_begin=0, row_stride=rows_step, row_block=1)
     dt = time.time() - t0
@@ -115,7 +122,7 @@ def run_reference(args):
     sc = scenes.make_scene(mm, args.config, assets)
     cores = os.cpu_count()
     rows_step = max(1, int(sc["W"] * sc["H"] / 150e3))     # ~150k pixels per step
-    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"])
+    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(ob, args.filter))
     times = []
     npx = len(range(0, sc["H"], rows_step)) * sc["W"]
     for i in range(args.warmup + args.steps):
@@ -131,7 +138,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_full_frame_extrapolated": sc["W"] * sc["H"] / v / 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config} {sc['W']}x{sc['H']} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
-                   "filter": "oracle FP32 sampler", "l2": "n/a (CPU)", "parallelism": f"{cores} host threads"},
+                   "filter": "oracle, texture-unit model sampler" if args.filter == "hw" else "oracle, binary32 sampler", "l2": "n/a (CPU)", "parallelism": f"{cores} host threads"},
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle port of compute-clouds.comp; stands in for the reference shader on lavapipe, which cannot run here"},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -318,7 +325,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             rows_step = max(1, int(W * H / 300e3))
-            wq = workload_Q(ob, sc, rows_step)
+            wq = workload_Q(ob, sc, rows_step, args.filter)
             texpeak = N_SM * TEXPEAK_QUADS_PER_CLK_PER_SM * peaks["sm_max_mhz"] * 1e6
             achieved = wq["Q"] * W * H / (ms * 1e-3)
             out["roofline"] = {"bound": "tex", "achieved": achieved / 1e9, "peak": texpeak / 1e9, "unit": "Gquad/s", "frac": achieved / texpeak,

@@ -122,6 +122,32 @@ MM_API int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun
 /* ---- HDR -> RGBA8 (tonemap.frag:11-28, vignette omitted) of the bound output; device or host dst */
 MM_API int mm_tonemap_rgba8(mm_ctx *ctx, uint8_t *dst, int dst_is_device, void *stream);
 
+/* ---- post chain: replaces the three PostProcessShader passes that consume the cloud image
+ * (Shader.h:460-520; VulkanApplication.cpp:309-317 construction, :943-968 and :1016 recording):
+ *     god-ray.frag:41-76 -> radialBlur.frag:36-63 -> tonemap.frag:11-33 -> swapchain (B8G8R8A8_UNORM, :1436-1446).
+ * camera160 carries view AND proj here (the passes project sun.location to the screen).  Images are DEVICE memory,
+ * pitch-linear: RGBA32F (16-byte aligned) or 8-bit RGBA/BGRA.  Source and destination must differ.
+ *   mm_god_ray / mm_radial_blur / mm_tonemap_present  one reference pass each (framebuffer in, framebuffer out)
+ *   mm_post_chain                                     the whole chain in two kernels, byte-identical to running the
+ *                                                     three passes in sequence: cloud image in, swapchain bytes out */
+MM_API int mm_god_ray(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src_rgba32f, size_t src_pitch,
+                      float *dst_rgba32f, size_t dst_pitch, int w, int h, void *stream);
+MM_API int mm_radial_blur(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src_rgba32f, size_t src_pitch,
+                          float *dst_rgba32f, size_t dst_pitch, int w, int h, void *stream);
+MM_API int mm_tonemap_present(mm_ctx *ctx, const float *src_rgba32f, size_t src_pitch, uint8_t *dst_8888, size_t dst_pitch,
+                              int w, int h, int bgra, void *stream);
+MM_API int mm_post_chain(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src_rgba32f, size_t src_pitch,
+                         uint8_t *dst_8888, size_t dst_pitch, int w, int h, int bgra, void *stream);
+
+/* ---- cloud shadows: the 6-step march of the low-res cloud field that the mesh shader runs per fragment
+ * (model.frag:240-283, helpers :58-140) as a standalone pass over n world positions (fragPositionWC): a G-buffer
+ * position image or a shadow-map grid.  Uses the uniforms of mm_set_uniforms (camera view + position, sun basis,
+ * wind) and the bound cloudPlacement / lowResCloudShape textures; the filter mode selects the sampler.
+ * out_density[i] = accumDensity of model.frag:266-272; the shader applies it as color *= 1 - 2*accumDensity (:281).
+ * on_device != 0: all pointers are device memory and the launch is asynchronous on `stream`; otherwise host arrays. */
+MM_API int mm_cloud_shadow(mm_ctx *ctx, const float *positions_xyz, int n, int on_device, float *out_density,
+                           uint32_t *out_fetches /* optional */, void *stream);
+
 /* ---- diagnostics: per-pixel work counters {loop trips, 2D fetches, 3D fetches, lit steps}
  * (uint32 x4 per pixel, device memory owned by the context; NULL disables).  Algorithmic counts:
  * what compute-clouds.comp would execute, whether or not the kernel skipped the work. */

@@ -34,6 +34,15 @@ float om_cloudLayerDensity(float relativeHeight, float cloudType);
 float om_heightBiasCoverage(float coverage, float height);
 int om_raySphereIntersection(const float ro[3], const float rd[3], const float sphere[4], float *t);
 
+/* cloud shadow march of the mesh shader (model.frag:240-283) for n world positions; fetches: texture() calls per point or NULL */
+int om_cloud_shadow(const om_scene *s, const float *positions_xyz, int n, float *out_density, uint32_t *fetches, int nthreads);
+
+/* post_chain_oracle.c: god-ray.frag:41-76, radialBlur.frag:36-63, tonemap.frag:11-33 */
+void om_sun_screen_position(const void *camera160, const void *sun116, float out_xy[2]);
+int om_god_ray(const void *camera160, const void *sun116, const float *src_rgba32f, int W, int H, float *dst_rgba32f);
+int om_radial_blur(const void *camera160, const void *sun116, const float *src_rgba32f, int W, int H, float *dst_rgba32f);
+int om_tonemap_present(const float *src_rgba32f, int W, int H, int bgra, uint8_t *dst_8888);
+
 /* reproject_oracle.c: restatement of reproject.comp:91-152 */
 int om_reproject(const void *camera160, const void *cameraPrev160, const float *src_rgba32f, int W, int H, float *dst_rgba32f);
 

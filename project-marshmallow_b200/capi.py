@@ -68,6 +68,11 @@ def load_library():
         "mm_dispatch_reproject": (i32, [vp, vp]),
         "mm_render_to_host": (i32, [vp, vp, vp, vp, i32, vp]),
         "mm_tonemap_rgba8": (i32, [vp, vp, i32, vp]),
+        "mm_god_ray": (i32, [vp, vp, vp, vp, sz, vp, sz, i32, i32, vp]),
+        "mm_radial_blur": (i32, [vp, vp, vp, vp, sz, vp, sz, i32, i32, vp]),
+        "mm_tonemap_present": (i32, [vp, vp, sz, vp, sz, i32, i32, i32, vp]),
+        "mm_post_chain": (i32, [vp, vp, vp, vp, sz, vp, sz, i32, i32, i32, vp]),
+        "mm_cloud_shadow": (i32, [vp, vp, i32, i32, vp, vp, vp]),
         "mm_enable_counters": (i32, [vp, i32]),
         "mm_read_counters": (i32, [vp, vp]),
         "mm_read_output": (i32, [vp, vp]),

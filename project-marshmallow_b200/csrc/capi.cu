@@ -55,6 +55,8 @@ struct mm_ctx {
     float *scratch = nullptr;      // curl-noise scratch
     uchar4 *stage = nullptr;       // upload staging (device)
     size_t stage_bytes = 0;
+    float *post_plane = nullptr;   // god-ray alpha plane of mm_post_chain
+    size_t post_plane_bytes = 0;
     char err[512];
 };
 
@@ -138,6 +140,7 @@ int mm_destroy(mm_ctx *ctx) {
     release_output(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->post_plane) cudaFree(ctx->post_plane);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -516,6 +519,148 @@ int mm_tonemap_rgba8(mm_ctx *ctx, uint8_t *dst, int dst_is_device, void *stream_
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     cudaFree(tmp);
     if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_tonemap_rgba8: %s", cudaGetErrorString(e));
+    return MM_OK;
+}
+
+// ---- post chain (god-ray.frag, radialBlur.frag, tonemap.frag) ------------------------------------------------------
+// (proj * view) * sun.location and the perspective divide (god-ray.frag:44-46, radialBlur.frag:48-49): uniform per
+// frame, evaluated here in the oracle's order -- mat4*mat4 then mat4*vec4, ((m0*v0 + m1*v1) + m2*v2) + m3*v3 per
+// component, binary32, no contraction (volatile keeps the host compiler from fusing or reassociating).
+static float dot4_ordered(float a0, float b0, float a1, float b1, float a2, float b2, float a3, float b3) {
+    volatile float p0 = a0 * b0, p1 = a1 * b1, p2 = a2 * b2, p3 = a3 * b3;
+    volatile float s = p0 + p1;
+    s = s + p2;
+    s = s + p3;
+    return s;
+}
+static void post_params(const float *cam, const float *sun, PostParams &p) {
+    const float *V = cam, *P = cam + 16;
+    float PV[16], r[4];
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++)
+            PV[j * 4 + i] = dot4_ordered(P[0 * 4 + i], V[j * 4 + 0], P[1 * 4 + i], V[j * 4 + 1], P[2 * 4 + i], V[j * 4 + 2], P[3 * 4 + i], V[j * 4 + 3]);
+    for (int i = 0; i < 4; i++) r[i] = dot4_ordered(PV[0 * 4 + i], sun[0], PV[1 * 4 + i], sun[1], PV[2 * 4 + i], sun[2], PV[3 * 4 + i], sun[3]);
+    volatile float sx = r[0] / r[3], sy = r[1] / r[3];
+    p.sun_x = sx; p.sun_y = sy;
+    p.sun_dir_y = sun[5];
+    for (int k = 0; k < 3; k++) { volatile float c = sun[8 + k] * sun[28]; p.sun_rgb[k] = c; }
+}
+
+static int post_check(mm_ctx *ctx, const char *who, const void *cam, const void *sun, const void *src, size_t src_pitch, const void *dst, size_t dst_pitch,
+                      size_t dst_texel, int w, int h) {
+    if (!ctx) return MM_ERR_ARG;
+    if ((!cam || !sun) && who[3] != 'p') return fail(ctx, MM_ERR_ARG, "%s: camera and sun blocks are required", who);
+    if (!src || !dst || w <= 0 || h <= 0) return fail(ctx, MM_ERR_ARG, "%s: null image or empty extent", who);
+    if (src == dst) return fail(ctx, MM_ERR_ARG, "%s: the pass reads neighbours of the pixel it writes; source and destination must differ", who);
+    if (((uintptr_t)src & 15) || (src_pitch & 15) || src_pitch < (size_t)w * 16) return fail(ctx, MM_ERR_ARG, "%s: source needs 16-byte alignment and pitch >= 16*w", who);
+    if (((uintptr_t)dst & (dst_texel - 1)) || (dst_pitch & (dst_texel - 1)) || dst_pitch < (size_t)w * dst_texel)
+        return fail(ctx, MM_ERR_ARG, "%s: destination needs %zu-byte alignment and pitch >= %zu*w", who, dst_texel, dst_texel);
+    return MM_OK;
+}
+
+int mm_god_ray(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src, size_t src_pitch, float *dst, size_t dst_pitch, int w, int h, void *stream_v) {
+    int rc = post_check(ctx, "mm_god_ray", camera160, sun116, src, src_pitch, dst, dst_pitch, 16, w, h);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    PostParams p = {};
+    post_params((const float *)camera160, (const float *)sun116, p);
+    p.src = src; p.src_pitch = src_pitch; p.dst = dst; p.dst_pitch = dst_pitch; p.W = w; p.H = h;
+    CU(launch_post(POST_GOD_RAY, p, stream_v ? (cudaStream_t)stream_v : ctx->stream));
+    return MM_OK;
+}
+
+int mm_radial_blur(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src, size_t src_pitch, float *dst, size_t dst_pitch, int w, int h, void *stream_v) {
+    int rc = post_check(ctx, "mm_radial_blur", camera160, sun116, src, src_pitch, dst, dst_pitch, 16, w, h);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    PostParams p = {};
+    post_params((const float *)camera160, (const float *)sun116, p);
+    p.src = src; p.src_pitch = src_pitch; p.dst = dst; p.dst_pitch = dst_pitch; p.W = w; p.H = h;
+    CU(launch_post(POST_RADIAL_BLUR, p, stream_v ? (cudaStream_t)stream_v : ctx->stream));
+    return MM_OK;
+}
+
+int mm_tonemap_present(mm_ctx *ctx, const float *src, size_t src_pitch, uint8_t *dst8, size_t dst_pitch, int w, int h, int bgra, void *stream_v) {
+    int rc = post_check(ctx, "mm_present", nullptr, nullptr, src, src_pitch, dst8, dst_pitch, 4, w, h);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    PostParams p = {};
+    p.src = src; p.src_pitch = src_pitch; p.dst8 = dst8; p.dst8_pitch = dst_pitch; p.W = w; p.H = h; p.bgra = bgra != 0;
+    CU(launch_post(POST_PRESENT, p, stream_v ? (cudaStream_t)stream_v : ctx->stream));
+    return MM_OK;
+}
+
+int mm_post_chain(mm_ctx *ctx, const void *camera160, const void *sun116, const float *src, size_t src_pitch, uint8_t *dst8, size_t dst_pitch, int w, int h,
+                  int bgra, void *stream_v) {
+    int rc = post_check(ctx, "mm_post_chain", camera160, sun116, src, src_pitch, dst8, dst_pitch, 4, w, h);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    size_t need = (size_t)w * h * 4;
+    if (ctx->post_plane_bytes < need) {                      // god-ray alpha plane, kept for the next frame
+        if (ctx->post_plane) { CU(cudaFree(ctx->post_plane)); ctx->post_plane = nullptr; ctx->post_plane_bytes = 0; }
+        CU(cudaMalloc(&ctx->post_plane, need));
+        ctx->post_plane_bytes = need;
+    }
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    PostParams p = {};
+    post_params((const float *)camera160, (const float *)sun116, p);
+    p.src = src; p.src_pitch = src_pitch; p.plane = ctx->post_plane; p.plane_pitch = (size_t)w * 4;
+    p.dst8 = dst8; p.dst8_pitch = dst_pitch; p.W = w; p.H = h; p.bgra = bgra != 0;
+    CU(cudaEventRecord(ctx->ev0, stream));
+    CU(launch_post(POST_GOD_RAY_ALPHA, p, stream));
+    CU(launch_post(POST_BLUR_PRESENT, p, stream));
+    CU(cudaEventRecord(ctx->ev1, stream));
+    ctx->timed = true;
+    return MM_OK;
+}
+
+// ---- cloud-shadow march of the mesh shader (model.frag:240-283) ------------------------------------------------------
+int mm_cloud_shadow(mm_ctx *ctx, const float *positions_xyz, int n, int on_device, float *out_density, uint32_t *out_fetches, void *stream_v) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!positions_xyz || !out_density || n < 0) return fail(ctx, MM_ERR_ARG, "mm_cloud_shadow: null array or negative count");
+    if (!ctx->have_uniforms) return fail(ctx, MM_ERR_STATE, "mm_cloud_shadow: no uniforms set (mm_set_uniforms)");
+    if (!ctx->tex[TEX_PLACEMENT].obj || !ctx->tex[TEX_LOWRES].obj) return fail(ctx, MM_ERR_STATE, "mm_cloud_shadow: cloudPlacement and lowResCloudShape must be bound");
+    if (n == 0) return MM_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    ShadowParams p = {};
+    memcpy(p.cam, ctx->cam, sizeof p.cam); memcpy(p.sun, ctx->sun, sizeof p.sun); memcpy(p.sky, ctx->sky, sizeof p.sky);
+    {   // L = normalize((camera.view * vec4(sun.directionBasis[1].xyz, 0)).xyz); if (L.y < -0.05) L *= -1  (model.frag:216-217)
+        const float *c = ctx->cam, *d = ctx->sun + 16;
+        float l[3];
+        for (int i = 0; i < 3; i++) l[i] = dot4_ordered(c[0 + i], d[0], c[4 + i], d[1], c[8 + i], d[2], c[12 + i], 0.0f);
+        volatile float xx = l[0] * l[0], yy = l[1] * l[1], zz = l[2] * l[2];
+        volatile float dd = xx + yy;
+        dd = dd + zz;
+        volatile float inv = 1.0f / sqrtf(dd);
+        for (int i = 0; i < 3; i++) { volatile float v = l[i] * inv; p.L[i] = v; }
+        if (p.L[1] < -0.05f) for (int i = 0; i < 3; i++) { volatile float v = -1.0f * p.L[i]; p.L[i] = v; }
+    }
+    const int slots[2] = {TEX_PLACEMENT, TEX_LOWRES};
+    TexDev *td[2] = {&p.placement, &p.lowres};
+    for (int k = 0; k < 2; k++) {
+        const TexSlot &s = ctx->tex[slots[k]];
+        *td[k] = TexDev{s.pairs, s.obj, s.w, s.h, s.d, (float)s.w, (float)s.h, (float)s.d, is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d)};
+    }
+    p.n = n;
+    if (on_device) {
+        p.pos = positions_xyz; p.out = out_density; p.fetches = out_fetches;
+        CU(cudaEventRecord(ctx->ev0, stream));
+        CU(launch_cloud_shadow(p, ctx->filter == MM_FILTER_HW ? FILTER_HW : FILTER_EXACT, stream));
+        CU(cudaEventRecord(ctx->ev1, stream));
+        ctx->timed = true;
+        return MM_OK;
+    }
+    float *d = nullptr;
+    CU(cudaMalloc(&d, (size_t)n * 20 + 16));                 // positions (12 B) + density (4 B) + fetches (4 B) per point
+    p.pos = d; p.out = d + 3 * (size_t)n; p.fetches = out_fetches ? reinterpret_cast<uint32_t *>(d + 4 * (size_t)n) : nullptr;
+    cudaError_t e = cudaMemcpyAsync(d, positions_xyz, (size_t)n * 12, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = launch_cloud_shadow(p, ctx->filter == MM_FILTER_HW ? FILTER_HW : FILTER_EXACT, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_density, p.out, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess && out_fetches) e = cudaMemcpyAsync(out_fetches, p.fetches, (size_t)n * 4, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_cloud_shadow: %s", cudaGetErrorString(e));
     return MM_OK;
 }
 

@@ -59,6 +59,33 @@ struct ReprojectParams {
     float *dst; size_t dst_pitch;         // targetImage
     int W, H;
 };
+// K6 post chain (post_chain.cu): god-ray.frag / radialBlur.frag / tonemap.frag.  The sun's screen position
+// ((proj*view)*sun.location, divided by w) and sun.color.xyz*sun.intensity are uniform per frame and evaluated on the
+// host in the oracle's binary32 order (capi.cu, post_params).
+struct PostParams {
+    const float *src; size_t src_pitch;       // RGBA32F input of the pass (pitch-linear float4)
+    float *dst; size_t dst_pitch;             // RGBA32F output (pass-by-pass kernels)
+    float *plane; size_t plane_pitch;         // god-ray alpha plane (fused chain): written by pass 1, tapped by pass 2
+    unsigned char *dst8; size_t dst8_pitch;   // UNORM8 output (present / fused chain)
+    float sun_x, sun_y, sun_dir_y;
+    float sun_rgb[3];
+    int W, H, bgra;
+};
+enum { POST_GOD_RAY = 0, POST_GOD_RAY_ALPHA = 1, POST_RADIAL_BLUR = 2, POST_BLUR_PRESENT = 3, POST_PRESENT = 4 };
+cudaError_t launch_post(int which, const PostParams &p, cudaStream_t stream);
+
+// K7 cloud-shadow march of the mesh shader (model.frag:240-283) for n world positions (cloud_march.cu)
+struct ShadowParams {
+    float cam[40], sun[29], sky[13];
+    float L[3];                               // view-space sun direction, flipped when L.y < -0.05 (model.frag:216-217); host
+    TexDev placement, lowres;
+    const float *pos;                         // n x (x, y, z) world positions (fragPositionWC)
+    float *out;                               // n x accumDensity
+    uint32_t *fetches;                        // optional: texture() calls per point
+    int n;
+};
+cudaError_t launch_cloud_shadow(const ShadowParams &p, int filter, cudaStream_t stream);
+
 cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, cudaStream_t stream);
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);

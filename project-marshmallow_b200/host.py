@@ -197,6 +197,46 @@ class ComputeShader:
         self._check(self._lib.mm_tonemap_rgba8(self._ctx, _ptr(out), 0, None))
         return out
 
+    # ---- post chain (PostProcessShader x3: god-ray.frag, radialBlur.frag, tonemap.frag); device pointers as integers
+    @staticmethod
+    def _stream(stream):
+        return None if stream is None else C.c_void_p(int(stream) if int(stream) != 0 else 1)
+
+    def godRay(self, cam, sun, src_ptr, dst_ptr, extent=None, src_pitch=None, dst_pitch=None, stream=None):
+        w, h = extent or (self.width, self.height)
+        cam, sun = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(sun, np.float32)
+        self._check(self._lib.mm_god_ray(self._ctx, _ptr(cam), _ptr(sun), C.c_void_p(int(src_ptr)), src_pitch or w * 16,
+                                         C.c_void_p(int(dst_ptr)), dst_pitch or w * 16, w, h, self._stream(stream)))
+
+    def radialBlur(self, cam, sun, src_ptr, dst_ptr, extent=None, src_pitch=None, dst_pitch=None, stream=None):
+        w, h = extent or (self.width, self.height)
+        cam, sun = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(sun, np.float32)
+        self._check(self._lib.mm_radial_blur(self._ctx, _ptr(cam), _ptr(sun), C.c_void_p(int(src_ptr)), src_pitch or w * 16,
+                                             C.c_void_p(int(dst_ptr)), dst_pitch or w * 16, w, h, self._stream(stream)))
+
+    def tonemapPresent(self, src_ptr, dst8_ptr, extent=None, src_pitch=None, dst_pitch=None, bgra=False, stream=None):
+        w, h = extent or (self.width, self.height)
+        self._check(self._lib.mm_tonemap_present(self._ctx, C.c_void_p(int(src_ptr)), src_pitch or w * 16, C.c_void_p(int(dst8_ptr)),
+                                                 dst_pitch or w * 4, w, h, int(bgra), self._stream(stream)))
+
+    def postChain(self, cam, sun, src_ptr, dst8_ptr, extent=None, src_pitch=None, dst_pitch=None, bgra=False, stream=None):
+        """cloud image (RGBA32F) -> swapchain bytes: god rays, radial blur, tone map + vignette in two kernels"""
+        w, h = extent or (self.width, self.height)
+        cam, sun = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(sun, np.float32)
+        self._check(self._lib.mm_post_chain(self._ctx, _ptr(cam), _ptr(sun), C.c_void_p(int(src_ptr)), src_pitch or w * 16,
+                                            C.c_void_p(int(dst8_ptr)), dst_pitch or w * 4, w, h, int(bgra), self._stream(stream)))
+
+    # ---- cloud shadows (the mesh shader's 6-step march, model.frag:240-283) for an array of world positions
+    def cloudShadow(self, positions, want_fetches=False):
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        out = np.empty(pos.shape[0], np.float32)
+        nf = np.empty(pos.shape[0], np.uint32) if want_fetches else None
+        self._check(self._lib.mm_cloud_shadow(self._ctx, _ptr(pos), pos.shape[0], 0, _ptr(out), _ptr(nf) if want_fetches else None, None))
+        return (out, nf) if want_fetches else out
+
+    def cloudShadowDevice(self, pos_ptr, n, out_ptr, stream=None):
+        self._check(self._lib.mm_cloud_shadow(self._ctx, C.c_void_p(int(pos_ptr)), int(n), 1, C.c_void_p(int(out_ptr)), None, self._stream(stream)))
+
     # ---- diagnostics
     def enableCounters(self, on=True):
         self._check(self._lib.mm_enable_counters(self._ctx, int(on)))

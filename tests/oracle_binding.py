@@ -40,6 +40,11 @@ def lib():
         l.om_curl_hash_index.restype, l.om_curl_hash_index.argtypes = i32, [f32] * 3
         l.om_raySphereIntersection.argtypes = [vp, vp, vp, vp]
         l.om_reproject.argtypes = [vp, vp, vp, i32, i32, vp]
+        l.om_cloud_shadow.argtypes = [vp, vp, i32, vp, vp, i32]
+        l.om_sun_screen_position.argtypes = [vp, vp, vp]
+        l.om_god_ray.argtypes = [vp, vp, vp, i32, i32, vp]
+        l.om_radial_blur.argtypes = [vp, vp, vp, i32, i32, vp]
+        l.om_tonemap_present.argtypes = [vp, i32, i32, i32, vp]
         l.om_generate_curl_noise.argtypes = [vp]
         l.om_build_noise_volumes.argtypes = [C.c_uint64, vp, vp]
         l.om_noise_hash.restype, l.om_noise_hash.argtypes = C.c_uint32, [C.c_uint32] * 4
@@ -93,6 +98,14 @@ class Scene:
         assert self.l.om_sample(self.s, slot, filter_mode, _p(uvw), uvw.shape[0], _p(out)) == 0
         return out
 
+    def cloud_shadow(self, positions, want_fetches=False, nthreads=0):
+        """model.frag:240-283 for an array of world positions -> accumDensity per point"""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        out = np.empty(pos.shape[0], np.float32)
+        nf = np.empty(pos.shape[0], np.uint32) if want_fetches else None
+        assert self.l.om_cloud_shadow(self.s, _p(pos), pos.shape[0], _p(out), _p(nf), nthreads) == 0
+        return (out, nf) if want_fetches else out
+
     def close(self):
         if self.s:
             self.l.om_scene_destroy(self.s)
@@ -115,6 +128,38 @@ def reproject(cam, cam_prev, src):
     H, W, _ = src.shape
     dst = np.empty_like(src)
     assert lib().om_reproject(_p(cam), _p(cam_prev), _p(src), W, H, _p(dst)) == 0
+    return dst
+
+
+def sun_screen_position(cam, sun):
+    cam, sun = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(sun, np.float32)
+    out = np.zeros(2, np.float32)
+    lib().om_sun_screen_position(_p(cam), _p(sun), _p(out))
+    return out
+
+
+def _post(fn, cam, sun, src):
+    cam, sun = np.ascontiguousarray(cam, np.float32), np.ascontiguousarray(sun, np.float32)
+    src = np.ascontiguousarray(src, np.float32)
+    H, W, _ = src.shape
+    dst = np.empty_like(src)
+    assert fn(_p(cam), _p(sun), _p(src), W, H, _p(dst)) == 0
+    return dst
+
+
+def god_ray(cam, sun, src):
+    return _post(lib().om_god_ray, cam, sun, src)
+
+
+def radial_blur(cam, sun, src):
+    return _post(lib().om_radial_blur, cam, sun, src)
+
+
+def tonemap_present(src, bgra=False):
+    src = np.ascontiguousarray(src, np.float32)
+    H, W, _ = src.shape
+    dst = np.empty((H, W, 4), np.uint8)
+    assert lib().om_tonemap_present(_p(src), W, H, int(bgra), _p(dst)) == 0
     return dst
 
 

@@ -73,7 +73,8 @@ def test_hw_sampler_is_the_texunit_model(mm, oracle, assets):
     tex = {"placement": assets["placement"], "curl": assets["curl"], "lowres": assets["lowres"], "hires": assets["hires"]}
     S = oracle.Scene(tex, np.zeros(40, np.float32), np.zeros(29, np.float32), np.zeros(13, np.float32), nightsky=star)
     cs = mm.ComputeShader(0, (8, 8), placement=tex["placement"], curl=tex["curl"], lowRes=tex["lowres"], hiRes=tex["hires"], nightSky=star)
-    for slot, lo, hi in ((mm.MM_TEX_PLACEMENT, -2, 2), (mm.MM_TEX_CURL, -20, 20), (mm.MM_TEX_LOWRES, -4, 4), (mm.MM_TEX_HIRES, -80, 80)):
+    for slot, lo, hi in ((mm.MM_TEX_PLACEMENT, -2, 2), (mm.MM_TEX_CURL, -20, 20), (mm.MM_TEX_LOWRES, -4, 4), (mm.MM_TEX_HIRES, -80, 80),
+                         (mm.MM_TEX_NIGHTSKY, -3, 3)):
         uvw = rng.uniform(lo, hi, (200000, 3)).astype(np.float32)
         uvw[:64] = np.float32([[i / 128.0, i / 64.0 - 0.25, 1.0 - i / 32.0] for i in range(64)])   # texel centres / edges
         got = cs.sample(slot, mm.MM_FILTER_HW, uvw)

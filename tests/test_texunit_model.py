@@ -75,3 +75,33 @@ def test_texunit_weights_partition_unity_and_constants_are_fixed_points(oracle):
     out = t.sample(uvw)
     t.close()
     assert np.array_equal(out, (tex.reshape(-1, 4).astype(np.float64) * 257 / 65535.0).astype(np.float32))
+
+
+@pytest.mark.parametrize("name,is3d", [("n50x27", False), ("n5x3", False), ("n3x7", False), ("v5x6x7", True), ("v3x3x3", True)])
+def test_non_power_of_two_extents_match_the_hardware_recording(oracle, name, is3d):
+    """Random (non-dyadic) coordinates on non-power-of-two extents: reproduced only when the wrapped coordinate is kept
+    as a truncated 21-bit fraction (step 1 of the model)."""
+    g = np.load(GOLD)
+    t = _OneTex(oracle, g[f"npot_{name}_unit_tex"], oracle.OM_TEX_LOWRES if is3d else oracle.OM_TEX_NIGHTSKY)
+    for tag in ("unit", "wide", "far"):
+        if f"npot_{name}_{tag}_uvw" in g.files:
+            _check(t.sample(g[f"npot_{name}_{tag}_uvw"]), g[f"npot_{name}_{tag}_x16"], f"{name}/{tag}")
+    t.close()
+
+
+def test_star_map_sized_texture_matches_the_hardware_recording(oracle):
+    """1920x1080 (the reference's nightSkyMap extent): the probe's texels are regenerated from its seed
+    (tools/texprobe3.py) instead of being stored."""
+    g = np.load(GOLD)
+    rng = np.random.default_rng(77)
+    tex = {}
+    for name, shape in (("n50x27", (27, 50, 4)), ("n5x3", (3, 5, 4)), ("n1920x1080", (1080, 1920, 4))):
+        tex[name] = rng.integers(0, 256, shape, dtype=np.uint8)
+        if name != "n1920x1080":
+            for lo, hi in ((0.0, 1.0), (-3.0, 3.0), (-300.0, 300.0)):
+                rng.uniform(lo, hi, (150000, 3))
+    if not np.array_equal(tex["n50x27"], g["npot_n50x27_unit_tex"]):
+        pytest.skip("numpy's generator stream differs from the one that recorded the probe")
+    t = _OneTex(oracle, tex["n1920x1080"], oracle.OM_TEX_NIGHTSKY)
+    _check(t.sample(g["npot_n1920x1080_unit_uvw"]), g["npot_n1920x1080_unit_x16"], "n1920x1080")
+    t.close()

@@ -13,18 +13,23 @@ import _pkg, scenes, oracle_binding as ob
 CASES = [("C1", 96, 54, {}), ("C3", 96, 54, {}), ("C5b", 64, 36, {}), ("C1", 64, 36, {"time": 40.0, "wind": (0.6, 0.05, -1.2)}),
          ("C1", 64, 36, {"elevation": 0.75})]   # the last one is a NIGHT frame (sun below the horizon, CC:365-384)
 
-def main():
+def main(only=()):
     mm = _pkg.load_package()
     assets = scenes.load_assets()
-    out = os.path.join(ROOT, "tests", "golden", "frames")
-    os.makedirs(out, exist_ok=True)
-    for i, (name, W, H, over) in enumerate(CASES):
-        sc = scenes.make_scene(mm, name, assets, W=W, H=H, **over)
-        night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
-        img, cnt = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], nightsky=night).march(W, H)
-        np.savez_compressed(os.path.join(out, f"frame{i}_{name}_{W}x{H}.npz"), rgba32f=img, rgba8=ob.tonemap_rgba8(img), counters=cnt.astype(np.uint16),
-                            cam=sc["cam"], sun=sc["sun"], sky=sc["sky"], config=np.array(repr((name, W, H, over))))
-        print(i, name, W, H, over, "trips/px %.1f lit/px %.2f" % (cnt[..., 0].mean(), cnt[..., 3].mean()))
+    # frames/: oracle with the exact binary32 sampler (OM_FILTER_FP32); frames_texunit/: oracle with the bit-exact
+    # model of the B200 texture unit (OM_FILTER_TEXUNIT) -- the target of the hardware-sampler march (MM_FILTER_HW)
+    for sub, filt in (("frames", ob.OM_FILTER_FP32), ("frames_texunit", ob.OM_FILTER_TEXUNIT)):
+        if only and sub not in only:
+            continue
+        out = os.path.join(ROOT, "tests", "golden", sub)
+        os.makedirs(out, exist_ok=True)
+        for i, (name, W, H, over) in enumerate(CASES):
+            sc = scenes.make_scene(mm, name, assets, W=W, H=H, **over)
+            night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
+            img, cnt = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], nightsky=night, filter_mode=filt).march(W, H)
+            np.savez_compressed(os.path.join(out, f"frame{i}_{name}_{W}x{H}.npz"), rgba32f=img, rgba8=ob.tonemap_rgba8(img), counters=cnt.astype(np.uint16),
+                                cam=sc["cam"], sun=sc["sun"], sky=sc["sky"], config=np.array(repr((name, W, H, over))))
+            print(sub, i, name, W, H, over, "trips/px %.1f lit/px %.2f" % (cnt[..., 0].mean(), cnt[..., 3].mean()))
 
 if __name__ == "__main__":
-    main()
+    main(tuple(sys.argv[1:]))      # optional: which sub-directories to (re)generate

@@ -32,6 +32,14 @@ put("cube2_rand", None, d["D_ruvw"], d["D_rout"], 12000)
 put("cube4_rand", d["E_tex"], d["E_ruvw"], d["E_rout"], 12000)
 for name in ("placement", "curl", "lowres", "hires"):          # texels: tests/golden/assets
     put("asset_" + name, None, d[f"F_{name}_uvw"], d[f"F_{name}_out"], 12000)
+# non-power-of-two extents with random coordinates (tools/texprobe3.py): these fix the 21-bit coordinate fraction
+d3 = np.load(os.path.join(ROOT, "gpurun_out", "texprobe3.npz"))
+for name in ("n50x27", "n5x3", "n3x7", "v5x6x7", "v3x3x3"):
+    for tag in ("unit", "wide", "far"):
+        if f"{name}_{tag}_uvw" in d3.files:
+            put(f"npot_{name}_{tag}", d3[name + "_tex"] if tag == "unit" else None, d3[f"{name}_{tag}_uvw"], d3[f"{name}_{tag}_out"], 6000)
+# 1920x1080 star-map-sized texture: regenerate the texels from the probe's seed instead of storing 8 MB
+put("npot_n1920x1080_unit", None, d3["n1920x1080_unit_uvw"], d3["n1920x1080_unit_out"], 12000)
 path = os.path.join(ROOT, "tests", "golden", "texunit_probe.npz")
 np.savez_compressed(path, **out)
 print(path, os.path.getsize(path), "bytes")
