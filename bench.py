@@ -312,6 +312,37 @@ def main():
         e2e = {"value": W * H / dt / 1e6, "unit": "Mpix/s", "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": 328,
                "d2h_bytes_per_step": W * H * 16, "note": "mm_render_to_host: uniform blocks from host, RGBA32F frame back to pinned host memory"}
 
+    # ---- the reference's own per-frame cadence (VulkanApplication.cpp:1053-1071): reproject the previous image, then ONE
+    # compute-clouds dispatch = 1/16 of the pixels (phase k % 16), ping-pong.  Reported beside the headline, which marches
+    # EVERY pixel every frame (16 reference dispatches' worth of rays).
+    cadence = None
+    if world == 1:
+        ping = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        pong = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        cs.bindOutput(ping.data_ptr())
+        cs.dispatch(mm.MM_FULL, stream=stream.cuda_stream)
+        cur, prev = pong, ping
+        cev = []
+        for i in range(Wm + K):
+            sun_i = sc["sun"].copy()
+            sun_i[11] = float(i % 16)                                   # sun.color.a carries the pixel phase (CC:292)
+            cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sun_i)
+            cs.bindOutput(cur.data_ptr())
+            cs.bindPrevious(prev.data_ptr())
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            cs.dispatchReproject(stream=stream.cuda_stream)
+            cs.dispatch(mm.MM_PHASE16, stream=stream.cuda_stream)
+            e1.record(stream)
+            if i >= Wm:
+                cev.append((e0, e1))
+            cur, prev = prev, cur
+        torch.cuda.synchronize()
+        cms = sum(a.elapsed_time(b) for a, b in cev) / len(cev)
+        cadence = {"ms_per_frame": cms, "frames_per_s": 1e3 / cms, "launches_per_frame": 2,
+                   "note": "reference cadence: reprojection of the previous image + one MM_PHASE16 dispatch (1/16 of the pixels marched), ping-pong images, L2 flushed between frames"}
+
     if rank == 0:
         peaks, which = measured_peaks()
         import oracle_binding as ob
@@ -323,6 +354,8 @@ def main():
                        "filter": args.filter, "l2": "flushed (256 MB write between frames)", "parallelism": f"row-cyclic x{world}, row block {args.row_block}" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": K, "e2e": e2e,
         }
+        if cadence:
+            out["reference_cadence"] = cadence
         if not args.no_cpu_baseline:
             rows_step = max(1, int(W * H / 300e3))
             wq = workload_Q(ob, sc, rows_step, args.filter)
@@ -334,7 +367,9 @@ def main():
                                "hbm_floor_ms": W * H * 16 / (peaks["hbm_gbs"] * 1e9) * 1e3}
             # second roofline: the march is FP32 / instruction-issue bound.  Warp-instructions per frame of this
             # exact command come from the committed ncu capture (profiles/); peak = 148 SM x 4 schedulers x f_SM.
-            prof = os.path.join(ROOT, "profiles", f"r01_final_{args.filter}.summary.csv")
+            prof = os.path.join(ROOT, "profiles", f"r01b_{args.filter}.summary.csv")        # capture of the current kernel revision
+            if not os.path.exists(prof):
+                prof = os.path.join(ROOT, "profiles", f"r01_final_{args.filter}.summary.csv")
             if os.path.exists(prof) and args.config == "C2" and world == 1:
                 rows = {l.split(",")[0]: l.strip().split(",") for l in open(prof) if l.count(",") >= 2}
                 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -48,11 +48,15 @@ enum mm_dispatch_mode {
                                (compute-clouds.comp:291-301, VulkanApplication.cpp:1067-1071) */
 };
 
-/* sampler arithmetic (see DESIGN.md "sampler modes") */
+/* sampler arithmetic (see DESIGN.md "sampler modes").  Vulkan leaves linear-filter precision to the implementation;
+ * each mode is one definition of it, and each has a bit-exact CPU statement in oracle/ that its decisions are tested
+ * against (zero branch flips, bit-identical alpha). */
 enum mm_filter_mode {
-    MM_FILTER_EXACT = 0,    /* FP32 software filtering, bit-identical to the CPU oracle (parity grade) */
-    MM_FILTER_HW = 1,       /* cudaTextureObject hardware filtering (8-bit weights), every fetch */
-    MM_FILTER_HYBRID = 2    /* march decisions: EXACT; the 6 light-cone samples: hardware filtering */
+    MM_FILTER_EXACT = 0,    /* binary32 software filtering of every fetch (oracle sampler OM_FILTER_FP32) */
+    MM_FILTER_HW = 1,       /* DEFAULT: the texture unit filters every fetch (cudaTextureObject; 8-bit corner weights,
+                               UNORM16 result) -- what the reference shader gets on this GPU; oracle sampler
+                               OM_FILTER_TEXUNIT is a bit-exact integer model of the unit */
+    MM_FILTER_HYBRID = 2    /* march decisions: EXACT; the 6 light-cone samples: texture unit */
 };
 
 /* ---- context: replaces ComputeShader's constructor/destructor (Shader.h:338-353, Shader.cpp:633-645) */

@@ -51,7 +51,7 @@ struct mm_ctx {
     float *mirror = nullptr;       // set only for the duration of one mm_render_to_host dispatch
     uint32_t *counters = nullptr;
     bool counters_on = false;
-    int filter = FILTER_EXACT;
+    int filter = FILTER_HW;        // production default: texture-unit filtering (parity: the oracle's texture-unit model)
     float *scratch = nullptr;      // curl-noise scratch
     uchar4 *stage = nullptr;       // upload staging (device)
     size_t stage_bytes = 0;

@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
         auto placement = readFile(argv[1]), curl = readFile(argv[2]), low = readFile(argv[3]), hi = readFile(argv[4]);
         int W = std::atoi(argv[5]), H = std::atoi(argv[6]);
         float elevation = argc > 8 ? (float)std::atof(argv[8]) : 0.25f;
-        int filter = argc > 9 ? std::atoi(argv[9]) : MM_FILTER_HYBRID;
+        int filter = argc > 9 ? std::atoi(argv[9]) : MM_FILTER_HW;
         TextureData tp{placement.data(), 512, 512, 1}, tc{curl.data(), 128, 128, 1}, tl{low.data(), 128, 128, 128}, th{hi.data(), 32, 32, 32};
         ComputeShader computeShader(0, Extent2D{W, H}, tp, nullptr, tc, tl, th);
         computeShader.setFilterMode(filter);

@@ -24,7 +24,7 @@ WORKER = textwrap.dedent("""
     sc = scenes.make_scene(mm, "C1", assets, W=400, H=231)
     cs = mm.ComputeShader(rank, (400, 231), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
                           lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
-    cs.setFilterMode(mm.MM_FILTER_HYBRID)
+    cs.setFilterMode(mm.MM_FILTER_HW)            # the default production mode
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
     shared = mm.multigpu.SharedFrame(cs, rank, world, dist)
     dist.barrier()

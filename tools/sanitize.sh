@@ -1,6 +1,6 @@
 #!/bin/bash
 # compute-sanitizer pass over the kernels (run on the GPU box): memcheck + racecheck on a small frame of every mode,
-# the noise builds, the reprojection pass and the tonemap.  Output -> gpurun_out/sanitizer_*.log
+# the noise builds, the reprojection pass, the tonemap, the post chain and the cloud-shadow pass.  Output -> gpurun_out/sanitizer_*.log
 mkdir -p gpurun_out
 cat > /tmp/san_driver.py <<'PY'
 import sys, os
@@ -22,6 +22,19 @@ for counters in (False, True):
         cs.dispatch(mm.MM_FULL, 1, 3, 2)
         cs.synchronize()
 cs.tonemapRGBA8()
+import torch
+src = torch.rand((H, W, 4), device="cuda")
+fb1, fb2 = torch.empty_like(src), torch.empty_like(src)
+out8 = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+cs.godRay(sc["cam"], sc["sun"], src.data_ptr(), fb1.data_ptr())
+cs.radialBlur(sc["cam"], sc["sun"], fb1.data_ptr(), fb2.data_ptr())
+cs.tonemapPresent(fb2.data_ptr(), out8.data_ptr())
+cs.postChain(sc["cam"], sc["sun"], src.data_ptr(), out8.data_ptr(), bgra=True)
+cs.synchronize()
+pos = np.random.default_rng(0).uniform(-20000, 20000, (5000, 3)).astype(np.float32)
+for mode in (mm.MM_FILTER_EXACT, mm.MM_FILTER_HW):
+    cs.setFilterMode(mode)
+    cs.cloudShadow(pos, want_fetches=True)
 cs.buildCurlNoise()
 if "--volumes" in sys.argv:
     cs.buildNoiseVolumes(1)
