@@ -26,7 +26,8 @@ class MarshmallowError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(HERE, "libmarshmallow_b200.so")
+    """MM_LIBRARY overrides the in-tree build (used by tools/ to time build variants of the same source)."""
+    return os.environ.get("MM_LIBRARY") or os.path.join(HERE, "libmarshmallow_b200.so")
 
 
 def exported_symbols():

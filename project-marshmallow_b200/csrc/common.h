@@ -22,11 +22,17 @@ enum { TEX_PLACEMENT = 0, TEX_NIGHTSKY = 1, TEX_CURL = 2, TEX_LOWRES = 3, TEX_HI
 enum { FILTER_EXACT = 0, FILTER_HW = 1, FILTER_HYBRID = 2 };
 enum { DISPATCH_FULL = 0, DISPATCH_PHASE16 = 1 };
 
-// Pixel tile of one warp: MM_TILE_W x (32 / MM_TILE_W); a block is 2 x 2 warps.
+// Pixel tile of one warp: MM_TILE_W x (32 / MM_TILE_W); a block is MM_WARPS_X x MM_WARPS_Y warps.
 #ifndef MM_TILE_W
 #define MM_TILE_W 8
 #endif
-enum { TILE_W = MM_TILE_W, TILE_H = 32 / MM_TILE_W, BLOCK_W = 2 * TILE_W, BLOCK_H = 2 * TILE_H };
+#ifndef MM_WARPS_X
+#define MM_WARPS_X 2
+#endif
+#ifndef MM_WARPS_Y
+#define MM_WARPS_Y 2
+#endif
+enum { TILE_W = MM_TILE_W, TILE_H = 32 / MM_TILE_W, WARPS_X = MM_WARPS_X, WARPS_Y = MM_WARPS_Y, BLOCK_W = WARPS_X * TILE_W, BLOCK_H = WARPS_Y * TILE_H };
 
 struct MarchParams {
     float cam[40];   // UniformCameraObject (Shader.h:24-29)
