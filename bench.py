@@ -43,6 +43,7 @@ def parse():
                     help="hw (default): texture-unit filtering, parity against the oracle's bit-exact texture-unit model; "
                          "exact / hybrid: FP32 software filtering of the march samples, parity against the oracle's binary32 sampler")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trips", type=int, default=0, choices=[0, 1, 2], help="loop trips in flight per ray: 0 = chosen per dispatch (default), 1, 2 (scheduling only)")
     ap.add_argument("--row-block", type=int, default=4)
     ap.add_argument("--animation", type=int, default=0, help="frame-parallel wind animation of N frames (BASELINE config 5): frame k on rank k %% world")
     return ap.parse_args()
@@ -228,6 +229,7 @@ def main():
     cs = mm.ComputeShader(local, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
                           lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
     cs.setFilterMode(fmode)
+    cs.setTripsInFlight(args.trips)
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
 
     from project_marshmallow_b200 import multigpu
@@ -364,7 +366,7 @@ def main():
             "ms_per_step": ms, "ms_per_frame": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config} {W}x{H} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
-                       "filter": args.filter, "l2": "flushed (256 MB write between frames)", "parallelism": f"row-cyclic x{world}, row block {args.row_block}" if world > 1 else "single GPU"},
+                       "filter": args.filter, "trips_in_flight": args.trips or "per dispatch", "l2": "flushed (256 MB write between frames)", "parallelism": f"row-cyclic x{world}, row block {args.row_block}" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": K, "e2e": e2e,
         }
         if cadence:

@@ -104,6 +104,11 @@ MM_API int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *
  * the context's own stream).  Rows are partitioned in blocks of row_block rows; this call marches
  * block b when (b - row_begin) % row_stride == 0 and b >= row_begin (single GPU: 0,1,1). */
 MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
+/* scheduling knob, never changes results: loop trips evaluated per ray and iteration.  2 = the next trip is evaluated
+ * speculatively together with the current one (half the dependent-chain latency of a launch, ~5 % more density
+ * evaluations); 1 = one at a time; 0 (default) = chosen per dispatch from its size (small dispatches -- MM_PHASE16,
+ * row-sharded frames on several GPUs -- get 2). */
+MM_API int mm_set_trips_in_flight(mm_ctx *ctx, int trips);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
 MM_API int mm_synchronize(mm_ctx *ctx);
 

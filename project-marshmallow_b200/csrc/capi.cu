@@ -57,6 +57,7 @@ struct mm_ctx {
     size_t stage_bytes = 0;
     float *post_plane = nullptr;   // god-ray alpha plane of mm_post_chain
     size_t post_plane_bytes = 0;
+    int trips_in_flight = 0;       // mm_set_trips_in_flight: 0 = choose per dispatch, 1, 2
     char err[512];
 };
 
@@ -76,6 +77,10 @@ static int fail(mm_ctx *c, int code, const char *fmt, ...) {
         cudaError_t e_ = (call);                                                                    \
         if (e_ != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+
+#ifndef MM_DUAL_WAVES
+#define MM_DUAL_WAVES 6
+#endif
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
@@ -330,6 +335,13 @@ int mm_bind_output_external_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, int w, i
     return size_counters(ctx);
 }
 
+int mm_set_trips_in_flight(mm_ctx *ctx, int trips) {
+    if (!ctx) return MM_ERR_ARG;
+    if (trips < 0 || trips > 2) return fail(ctx, MM_ERR_ARG, "mm_set_trips_in_flight: %d (0 = per dispatch, 1, 2)", trips);
+    ctx->trips_in_flight = trips;
+    return MM_OK;
+}
+
 int mm_set_filter_mode(mm_ctx *ctx, int filter) {
     if (!ctx) return MM_ERR_ARG;
     if (filter < MM_FILTER_EXACT || filter > MM_FILTER_HYBRID) return fail(ctx, MM_ERR_ARG, "mm_set_filter_mode: unknown mode %d", filter);
@@ -416,7 +428,15 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
     order_block_rows(p, p.block_row_order, nblockrows);
     CU(cudaEventRecord(ctx->ev0, stream));
-    CU(launch_cloud_march(p, ctx->filter, stream));
+    // Two trips in flight per ray (cloud_march.cu, DUAL) halve the latency floor of a launch at ~5 % more cloudTest
+    // evaluations: chosen when the dispatch is too small to hide that floor behind other blocks (< MM_DUAL_WAVES waves
+    // of the 148 x 8 resident blocks), i.e. MM_PHASE16 dispatches and row-sharded frames on several GPUs.
+    bool dual = ctx->trips_in_flight == 2;
+    if (ctx->trips_in_flight == 0) {
+        long long blocks = (long long)((p.grid_w + BLOCK_W - 1) / BLOCK_W) * nblockrows;
+        dual = blocks < (long long)MM_DUAL_WAVES * 148 * 8;
+    }
+    CU(launch_cloud_march(p, ctx->filter, dual, stream));
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->timed = true;
     return MM_OK;

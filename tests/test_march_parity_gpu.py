@@ -11,13 +11,16 @@ import scenes
 
 pytestmark = pytest.mark.gpu
 
+_FILTERS = {"exact": ("MM_FILTER_EXACT", "OM_FILTER_FP32"), "hybrid": ("MM_FILTER_HYBRID", "OM_FILTER_FP32"), "hw": ("MM_FILTER_HW", "OM_FILTER_TEXUNIT")}
 
-def _render(mm, sc, filter_mode, mode=0, rows=(0, 1, 1), counters=True):
+
+def _render(mm, sc, filter_mode, mode=0, rows=(0, 1, 1), counters=True, trips=0):
     cs = mm.ComputeShader(0, (sc["W"], sc["H"]), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
                           lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
     cs.allocOutput()
     cs.enableCounters(counters)
     cs.setFilterMode(filter_mode)
+    cs.setTripsInFlight(trips)
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
     cs.dispatch(mode, *rows)
     cs.synchronize()
@@ -107,6 +110,42 @@ def test_hw_mode_matches_texunit_oracle(mm, oracle, assets, name, W, H):
     print(name, "hw production variant", rep2)
     assert rep2["alpha_identical_frac"] == 1.0
     assert rep2["max_abs_diff_8bit"] <= 2 and rep2["frac_within_1"] >= 0.999
+
+
+@pytest.mark.parametrize("name,W,H,over", [("C1", 320, 180, {}), ("C3", 256, 144, {}), ("C5b", 200, 113, {}),
+                                           ("C1", 192, 108, dict(time=123.5, wind=(0.7, 0.05, -1.3))), ("C1", 97, 61, dict(elevation=0.75))])
+@pytest.mark.parametrize("mode", ["hw", "exact", "hybrid"])
+def test_two_trips_in_flight_change_nothing(mm, oracle, assets, name, W, H, over, mode):
+    """mm_set_trips_in_flight(2) evaluates the next loop trip speculatively with the current one.  It is a scheduling
+    choice: the image (every bit of it, colour included), the counters and therefore every decision equal the
+    one-trip-at-a-time kernel, and both equal the oracle's counters."""
+    sc = scenes.make_scene(mm, name, assets, W=W, H=H, **over)
+    night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
+    kfilter, ofilter = getattr(mm, _FILTERS[mode][0]), getattr(oracle, _FILTERS[mode][1])
+    out = {}
+    for trips in (1, 2):
+        for counters in (True, False):
+            cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                                  lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"], nightSky=night)
+            cs.allocOutput()
+            cs.enableCounters(counters)
+            cs.setFilterMode(kfilter)
+            cs.setTripsInFlight(trips)
+            img = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+            out[trips, counters] = (img, cs.readCounters() if counters else None)
+            # one reference-style phase dispatch too
+            cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+            cs.dispatch(mm.MM_PHASE16)
+            cs.synchronize()
+            out[trips, counters, "p16"] = cs.readOutput()
+            cs.close()
+    for counters in (True, False):
+        assert np.array_equal(out[1, counters][0].view(np.uint32), out[2, counters][0].view(np.uint32))
+        assert np.array_equal(out[1, counters, "p16"].view(np.uint32), out[2, counters, "p16"].view(np.uint32))
+    assert np.array_equal(out[1, True][1], out[2, True][1])
+    _, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=ofilter, nightsky=night).march(W, H)
+    cols = [0, 3] if mode == "hybrid" else [0, 1, 2, 3]     # hybrid's light-cone samples are filtered differently from its oracle:
+    assert np.array_equal(out[2, True][1][..., cols], rcnt[..., cols])      # their fetch counts may differ, trips and lit steps may not
 
 
 def test_hw_mode_against_float_filter_oracle_reports_tail(mm, oracle, assets):
@@ -244,9 +283,6 @@ def test_exact_divide_by_constant_is_the_ieee_quotient(mm):
         which += 1
     cs.close()
     assert len(seen) >= 13          # 10 constants + sqrt + rcp + remapClampedTo1
-
-
-_FILTERS = {"exact": ("MM_FILTER_EXACT", "OM_FILTER_FP32"), "hybrid": ("MM_FILTER_HYBRID", "OM_FILTER_FP32"), "hw": ("MM_FILTER_HW", "OM_FILTER_TEXUNIT")}
 
 
 @pytest.mark.parametrize("name,mode", [("C2", "hw"), ("C3", "hw"), ("C2", "hybrid"), ("C2", "exact"), ("C3", "hybrid")])
