@@ -504,6 +504,10 @@ static inline v3 mat3mul(const float m[9], v3 v) {
               ((m[2] * v.x) + (m[5] * v.y)) + (m[8] * v.z));
 }
 
+/* test model of the kernel's ray-split mode: trips evaluated per window (1 = the plain reference loop) */
+static int g_window = 1;
+void om_set_window(int g) { g_window = (g < 1) ? 1 : (g > 32 ? 32 : g); }
+
 /* CC:288-500 for one target pixel.  W,H replace the hard-coded 1920x1080 (Q7, CC:283-285). */
 static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, float out[4], px_counters *cnt) {
     ctx_t cx; cx.s = s; cx.cnt = cnt;
@@ -596,6 +600,87 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
     v3 windXYZ = V3(sky[8], sky[9], sky[10]);
 
     float henyeyGreenstein = omaxf(hgPhase(cosTheta, 0.6f), 0.7f * hgPhase(cosTheta, 0.99f - 0.1f));   /* CC:407 */
+    if (g_window > 1) {
+        /*
+         * Windowed evaluation (test model of the CUDA kernel's ray-split mode, csrc/cloud_march.cu): cloudTest of G
+         * consecutive trips t, t+step, ... is evaluated up front (on the GPU: one lane each), cloudHiRes for those with
+         * density > 0 once the ray has had its first hit, and then the reference loop below is replayed over the window
+         * with those values.  An event that takes t or stepSize out of sequence (first hit, 10th miss, termination) ends
+         * the window; the rest of it is discarded.  Must equal the plain loop bit for bit for every G.
+         */
+        int G = g_window;
+        float t = tInner;
+        int alive = t < tOuter;
+        while (alive) {
+            float tj[32], D[32], Hh[32], hj[32]; v3 pj[32], wj[32];
+            unsigned long long evals = 0;
+            tj[0] = t;
+            for (int j = 1; j < G; j++) tj[j] = tj[j - 1] + stepSize;
+            px_counters scratch = {0, 0, 0, 0, NULL};
+            ctx_t cs = cx; cs.cnt = &scratch;                         /* speculative evaluations are counted at replay */
+            for (int j = 0; j < G; j++) {
+                if (!(tj[j] < tOuter)) { D[j] = 0.0f; Hh[j] = 0.0f; continue; }
+                pj[j] = add3(cameraPos, scale3(tj[j], rayDirection));
+                v3 proj = getProjectedShellPoint(pj[j], earthCenter);
+                hj[j] = getRelativeHeight(pj[j], proj, atmosphereThickness);
+                wj[j] = scale3((timeOffset + (hj[j] * 200.0f)), scale3(WIND_STRENGTH, add3(windXYZ, scale3(hj[j], V3(0.1f, 0.05f, 0.0f)))));
+                D[j] = cloudTest(&cs, add3(pj[j], wj[j]), hj[j]);
+                evals++;
+                Hh[j] = 0.0f;
+                if (!noHits && D[j] > 0.0f) Hh[j] = cloudHiRes(&cs, add3(pj[j], wj[j]), stepSize, D[j], hj[j]);
+            }
+            if (g_stats_on) { _Pragma("omp atomic") om_debug_stats[6]++; _Pragma("omp atomic") om_debug_stats[7] += evals; }
+            /* replay: the reference loop body, CC:408-482, over the window */
+            int k = 0, window_open = 1;
+            while (window_open) {
+                if (!(t < tOuter)) { alive = 0; break; }                          /* CC:408 loop condition */
+                cnt->trips++; cnt->n2d++; cnt->n3d++;
+                v3 currentPos = pj[k];
+                float rHeight = hj[k];
+                float density = D[k], loDensity = D[k];
+                int skipTail = 0, event = 0;
+                if (density > 0.0f) {
+                    misses = 0;
+                    if (noHits) {
+                        t -= stepSize; stepSize *= 0.3f; noHits = 0;
+                        skipTail = 1; event = 1;
+                    } else {
+                        density = Hh[k]; cnt->n2d++; cnt->n3d++;
+                        if (density < 0.0001f) skipTail = 1;
+                        else {
+                            cnt->lit++;
+                            float densityAlongLight = 0.0f;
+                            for (int i = 0; i < 6; i++) {
+                                v3 lsPos = add3(currentPos, scale3(3.0f * stepSize, samples[i]));
+                                v3 lsProj = getProjectedShellPoint(lsPos, earthCenter);
+                                float lsHeight = getRelativeHeight(lsPos, lsProj, atmosphereThickness);
+                                v3 lwo = scale3((timeOffset + (lsHeight * 200.0f)), scale3(WIND_STRENGTH, add3(windXYZ, scale3(lsHeight, V3(0.1f, 0.05f, 0.0f)))));
+                                float lsDensity = cloudTest(&cx, add3(lsPos, lwo), lsHeight);
+                                if (lsDensity > 0.0f) { lsDensity = cloudHiRes(&cx, add3(lsPos, lwo), stepSize, lsDensity, lsHeight); densityAlongLight += lsDensity; }
+                            }
+                            float beersLaw = expf(-densityAlongLight);
+                            float beersModulated = omaxf(beersLaw, 0.7f * expf(-0.25f * densityAlongLight));
+                            beersLaw = mixf(beersLaw, beersModulated, ((-cosTheta) * 0.5f) + 0.5f);
+                            float inScatter = 0.09f + powf(loDensity, remapClampedf(rHeight, 0.3f, 0.85f, 0.5f, 2.0f));
+                            inScatter *= powf(remapClampedf(rHeight, 0.07f, 0.34f, 0.1f, 1.0f), 0.8f);
+                            transmittance = mixf(transmittance, (inScatter * henyeyGreenstein) * beersLaw, (1.0f - accumDensity));
+                            accumDensity += density;
+                        }
+                    }
+                } else if (!noHits) {
+                    misses++;
+                    if (misses >= 10) { noHits = 1; stepSize /= 0.3f; event = 1; }
+                }
+                if (!skipTail) {
+                    if (accumDensity > 0.99f) { accumDensity = 1.0f; alive = 0; break; }
+                    if (++steps > MAX_STEPS) { alive = 0; break; }
+                }
+                t += stepSize;                                                    /* CC:408 increment (after `continue` too) */
+                k++;
+                if (event || k >= G) window_open = 0;
+            }
+        }
+    } else
     for (float t = tInner; t < tOuter; t += stepSize) {                           /* CC:408 */
         cnt->trips++;
         v3 currentPos = add3(cameraPos, scale3(t, rayDirection));

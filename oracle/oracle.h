@@ -21,6 +21,7 @@ int om_scene_set_uniforms(om_scene *s, const void *camera160, const void *sun116
 int om_scene_set_modes(om_scene *s, int filter, int pow_mode);
 int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_stride, int row_block,
              float *out_rgba32f, uint32_t *counters /* 4 per pixel or NULL */, int nthreads);
+void om_set_window(int trips_per_window /* 1 = plain loop; >1 = windowed replay model of the kernel's ray-split mode */);
 void om_set_litmask_buffer(uint32_t *buf /* 8 x uint32 per pixel (zeroed by the caller), or NULL */);
 int om_sample(const om_scene *s, int slot, int filter, const float *uvw, int n, float *out_rgba);
 void om_tonemap_rgba8(const float *rgba32f, size_t npix, uint8_t *rgba8);

@@ -63,7 +63,7 @@ def load_library():
         "mm_bind_output_external_fd": (i32, [vp, i32, sz, i32, i32]),
         "mm_alloc_output": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]),
         "mm_set_filter_mode": (i32, [vp, i32]),
-        "mm_set_trips_in_flight": (i32, [vp, i32]),
+        "mm_set_lanes_per_ray": (i32, [vp, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
         "mm_synchronize": (i32, [vp]),
         "mm_bind_previous_linear": (i32, [vp, vp, sz]),

@@ -57,7 +57,7 @@ struct mm_ctx {
     size_t stage_bytes = 0;
     float *post_plane = nullptr;   // god-ray alpha plane of mm_post_chain
     size_t post_plane_bytes = 0;
-    int trips_in_flight = 0;       // mm_set_trips_in_flight: 0 = choose per dispatch, 1, 2
+    int lanes_per_ray = 0;         // mm_set_lanes_per_ray: 0 = chosen per dispatch, 1, 2, 4, 8
     char err[512];
 };
 
@@ -78,8 +78,8 @@ static int fail(mm_ctx *c, int code, const char *fmt, ...) {
         if (e_ != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
-#ifndef MM_DUAL_WAVES
-#define MM_DUAL_WAVES 6
+#ifndef MM_SPLIT_WAVES
+#define MM_SPLIT_WAVES 3.0
 #endif
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -335,10 +335,11 @@ int mm_bind_output_external_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, int w, i
     return size_counters(ctx);
 }
 
-int mm_set_trips_in_flight(mm_ctx *ctx, int trips) {
+int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes) {
     if (!ctx) return MM_ERR_ARG;
-    if (trips < 0 || trips > 2) return fail(ctx, MM_ERR_ARG, "mm_set_trips_in_flight: %d (0 = per dispatch, 1, 2)", trips);
-    ctx->trips_in_flight = trips;
+    if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8)
+        return fail(ctx, MM_ERR_ARG, "mm_set_lanes_per_ray: %d (0 = per dispatch, 1, 2, 4, 8)", lanes);
+    ctx->lanes_per_ray = lanes;
     return MM_OK;
 }
 
@@ -365,12 +366,12 @@ static void light_cone_samples(const float *sun, float out[18]) {
 // Order the 8-row block rows of one dispatch by expected cost, descending.  Cost proxy: the ray through the
 // middle column of the block row's middle row; below the horizon (CC:351) it is free, otherwise the path
 // through the shell grows as the ray approaches the horizon, i.e. as rd.y falls.  Scheduling hint only.
-static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows) {
+static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows, int block_h) {
     const float *cam = p.cam;
     struct Key { float k; uint16_t i; };
     static thread_local Key keys[4096];
     for (int b = 0; b < nblockrows; b++) {
-        int j = b * BLOCK_H + BLOCK_H / 2, py;
+        int j = b * block_h + block_h / 2, py;
         if (p.mode == DISPATCH_PHASE16) py = j * 4;
         else { int k = j / p.row_block; py = (p.row_begin + k * p.row_stride) * p.row_block + (j - k * p.row_block); }
         if (py >= p.H) py = p.H - 1;
@@ -424,19 +425,23 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         p.owned_rows = (ctx->H + 3) / 4;
         p.grid_w = (ctx->W + 3) / 4;
     }
-    int nblockrows = (p.owned_rows + BLOCK_H - 1) / BLOCK_H;
-    if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
-    order_block_rows(p, p.block_row_order, nblockrows);
-    CU(cudaEventRecord(ctx->ev0, stream));
-    // Two trips in flight per ray (cloud_march.cu, DUAL) halve the latency floor of a launch at ~5 % more cloudTest
-    // evaluations: chosen when the dispatch is too small to hide that floor behind other blocks (< MM_DUAL_WAVES waves
-    // of the 148 x 8 resident blocks), i.e. MM_PHASE16 dispatches and row-sharded frames on several GPUs.
-    bool dual = ctx->trips_in_flight == 2;
-    if (ctx->trips_in_flight == 0) {
-        long long blocks = (long long)((p.grid_w + BLOCK_W - 1) / BLOCK_W) * nblockrows;
-        dual = blocks < (long long)MM_DUAL_WAVES * 148 * 8;
+    // Lanes per ray (cloud_march.cu, K1 / K1s): one thread per ray unless the dispatch is too small to hide the latency of a
+    // single ray behind other blocks.  A B200 keeps 148 x 1024 one-lane rays resident; below MM_SPLIT_WAVES times that, rays are
+    // split over 2, 4 or 8 lanes so that the launch has about that many waves again (MM_PHASE16 dispatches, row-sharded frames
+    // on several GPUs).  Scheduling only: every variant produces the same bits.
+    int lanes = ctx->lanes_per_ray;
+    if (lanes == 0) {
+        double waves = (double)p.grid_w * (double)p.owned_rows / (148.0 * 1024.0);
+        lanes = 1;
+        while (lanes < 8 && waves * lanes < MM_SPLIT_WAVES) lanes *= 2;
     }
-    CU(launch_cloud_march(p, ctx->filter, dual, stream));
+    int block_w, block_h;
+    march_block_shape(lanes, &block_w, &block_h);
+    int nblockrows = (p.owned_rows + block_h - 1) / block_h;
+    if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
+    order_block_rows(p, p.block_row_order, nblockrows, block_h);
+    CU(cudaEventRecord(ctx->ev0, stream));
+    CU(launch_cloud_march(p, ctx->filter, lanes, stream));
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->timed = true;
     return MM_OK;

@@ -153,9 +153,9 @@ class ComputeShader:
     def setFilterMode(self, mode):
         self._check(self._lib.mm_set_filter_mode(self._ctx, mode))
 
-    def setTripsInFlight(self, trips):
-        """0 = per dispatch (default), 1, 2: scheduling only, results are identical"""
-        self._check(self._lib.mm_set_trips_in_flight(self._ctx, trips))
+    def setLanesPerRay(self, lanes):
+        """0 = per dispatch (default), 1, 2, 4, 8: scheduling only, results are identical"""
+        self._check(self._lib.mm_set_lanes_per_ray(self._ctx, lanes))
 
     def dispatch(self, mode=capi.MM_FULL, row_begin=0, row_stride=1, row_block=1, stream=None):
         """stream: None -> the context's own stream; an integer cudaStream_t otherwise (0, the legacy default

@@ -20,7 +20,7 @@ def _render(mm, sc, filter_mode, mode=0, rows=(0, 1, 1), counters=True, trips=0)
     cs.allocOutput()
     cs.enableCounters(counters)
     cs.setFilterMode(filter_mode)
-    cs.setTripsInFlight(trips)
+    cs.setLanesPerRay(trips)
     cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
     cs.dispatch(mode, *rows)
     cs.synchronize()
@@ -115,37 +115,46 @@ def test_hw_mode_matches_texunit_oracle(mm, oracle, assets, name, W, H):
 @pytest.mark.parametrize("name,W,H,over", [("C1", 320, 180, {}), ("C3", 256, 144, {}), ("C5b", 200, 113, {}),
                                            ("C1", 192, 108, dict(time=123.5, wind=(0.7, 0.05, -1.3))), ("C1", 97, 61, dict(elevation=0.75))])
 @pytest.mark.parametrize("mode", ["hw", "exact", "hybrid"])
-def test_two_trips_in_flight_change_nothing(mm, oracle, assets, name, W, H, over, mode):
-    """mm_set_trips_in_flight(2) evaluates the next loop trip speculatively with the current one.  It is a scheduling
-    choice: the image (every bit of it, colour included), the counters and therefore every decision equal the
-    one-trip-at-a-time kernel, and both equal the oracle's counters."""
+def test_lanes_per_ray_change_nothing(mm, oracle, assets, name, W, H, over, mode):
+    """mm_set_lanes_per_ray(2|4|8) runs the ray-split kernel: G consecutive loop trips of a ray evaluated side by side and
+    replayed through the loop's state machine.  It is a scheduling choice: the image (every bit of it, colour included), the
+    counters and therefore every decision equal the one-thread-per-ray kernel, and all equal the oracle's counters."""
     sc = scenes.make_scene(mm, name, assets, W=W, H=H, **over)
     night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
     kfilter, ofilter = getattr(mm, _FILTERS[mode][0]), getattr(oracle, _FILTERS[mode][1])
     out = {}
-    for trips in (1, 2):
+    for lanes in (1, 2, 4, 8):
         for counters in (True, False):
             cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
                                   lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"], nightSky=night)
             cs.allocOutput()
             cs.enableCounters(counters)
             cs.setFilterMode(kfilter)
-            cs.setTripsInFlight(trips)
+            cs.setLanesPerRay(lanes)
             img = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
-            out[trips, counters] = (img, cs.readCounters() if counters else None)
-            # one reference-style phase dispatch too
-            cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+            out[lanes, counters] = (img, cs.readCounters() if counters else None)
+            cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])       # one reference-style phase dispatch too
             cs.dispatch(mm.MM_PHASE16)
+            cs.dispatch(mm.MM_FULL, 1, 3, 2)                                     # and a row-sharded partial frame on top of it
             cs.synchronize()
-            out[trips, counters, "p16"] = cs.readOutput()
+            out[lanes, counters, "p16"] = cs.readOutput()
             cs.close()
-    for counters in (True, False):
-        assert np.array_equal(out[1, counters][0].view(np.uint32), out[2, counters][0].view(np.uint32))
-        assert np.array_equal(out[1, counters, "p16"].view(np.uint32), out[2, counters, "p16"].view(np.uint32))
-    assert np.array_equal(out[1, True][1], out[2, True][1])
+    for lanes in (2, 4, 8):
+        for counters in (True, False):
+            assert np.array_equal(out[1, counters][0].view(np.uint32), out[lanes, counters][0].view(np.uint32)), (lanes, counters)
+            assert np.array_equal(out[1, counters, "p16"].view(np.uint32), out[lanes, counters, "p16"].view(np.uint32)), (lanes, counters)
+        assert np.array_equal(out[1, True][1], out[lanes, True][1]), lanes
     _, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=ofilter, nightsky=night).march(W, H)
     cols = [0, 3] if mode == "hybrid" else [0, 1, 2, 3]     # hybrid's light-cone samples are filtered differently from its oracle:
-    assert np.array_equal(out[2, True][1][..., cols], rcnt[..., cols])      # their fetch counts may differ, trips and lit steps may not
+    assert np.array_equal(out[8, True][1][..., cols], rcnt[..., cols])      # their fetch counts may differ, trips and lit steps may not
+
+
+@pytest.mark.parametrize("W,H", [(1, 1), (5, 3), (33, 9)])
+def test_lanes_per_ray_on_ragged_extents(mm, assets, W, H):
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    frames = [_render(mm, sc, mm.MM_FILTER_HW, counters=False, trips=lanes)[0] for lanes in (1, 2, 4, 8)]
+    for f in frames[1:]:
+        assert np.array_equal(f.view(np.uint32), frames[0].view(np.uint32))
 
 
 def test_hw_mode_against_float_filter_oracle_reports_tail(mm, oracle, assets):

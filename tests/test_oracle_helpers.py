@@ -137,3 +137,22 @@ def test_march_statistics_match_survey_probe(oracle, assets, mm):
     sc2 = scenes.make_scene(mm, "C1", assets, pitch=+30 * scenes.DEG2RAD)     # looking 30 degrees DOWN: all rays killed (CC:351)
     img2, cnt2 = oracle.Scene(sc2["textures"], sc2["cam"], sc2["sun"], sc2["sky"]).march(64, 36)
     assert cnt2.sum() == 0 and (img2[..., :3] > 0).all()
+
+
+def test_windowed_replay_model_equals_the_plain_loop(mm, oracle, assets):
+    """The construction behind the kernel's ray-split mode (G consecutive trips evaluated up front, the loop body replayed over
+    them, the window closed by the first event) as a CPU model inside the oracle: bit-identical frames and counters for every G."""
+    import scenes
+    lib = oracle.lib()
+    for name, filt in (("C1", oracle.OM_FILTER_TEXUNIT), ("C5b", oracle.OM_FILTER_FP32), ("C3", oracle.OM_FILTER_TEXUNIT)):
+        sc = scenes.make_scene(mm, name, assets, W=96, H=54)
+        S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=filt)
+        lib.om_set_window(1)
+        ref, rcnt = S.march(96, 54)
+        try:
+            for g in (2, 4, 8, 11, 32):
+                lib.om_set_window(g)
+                img, cnt = S.march(96, 54)
+                assert np.array_equal(img.view(np.uint32), ref.view(np.uint32)) and np.array_equal(cnt, rcnt), (name, g)
+        finally:
+            lib.om_set_window(1)

@@ -8,7 +8,7 @@ sc = scenes.make_scene(mm, sys.argv[2] if len(sys.argv) > 2 else "C2", assets)
 W, H = sc["W"], sc["H"]
 cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"], lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
 cs.allocOutput()
-cs.setTripsInFlight(int(sys.argv[1]))
+cs.setLanesPerRay(int(sys.argv[1]))
 cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
 for _ in range(4):
     cs.dispatch(mm.MM_PHASE16)
