@@ -137,6 +137,7 @@ float om_det_powf(float x, float y) {
 typedef struct {
     const float *texels;  /* w*h*d*4 floats holding the byte values 0..255 */
     int w, h, d;
+    const uint8_t *bytes; /* the same texels as bytes (integer sampler model) */
 } ftex;
 
 static inline int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
@@ -181,12 +182,12 @@ static inline void filter_coord(float u, int n, int filter, int *i0, int *i1, fl
  */
 static inline void texunit_coord(float u, int n, int *i0, int *i1, int *wq) {
     double f = (double)u - floor((double)u);
-    int64_t F = (int64_t)floor(f * 2097152.0);                               /* 21 fractional bits, truncated */
+    int64_t F = (int64_t)(f * 2097152.0);                                    /* 21 fractional bits, truncated (f >= 0) */
     int64_t num = ((F * (int64_t)n) * 256 - (128LL << 21)) + (1LL << 20);
     int64_t S = num >> 21;                                                   /* floor (arithmetic shift) */
     *wq = (int)(S & 255);
-    int64_t i = (S >> 8) % n;
-    if (i < 0) i += n;
+    int64_t i = S >> 8;                                                      /* -1 .. n */
+    if (i < 0) i += n; else if (i >= n) i -= n;
     *i0 = (int)i;
     *i1 = (i + 1 == n) ? 0 : (int)i + 1;
 }
@@ -210,10 +211,10 @@ static void texunit_sample(const ftex *t, int is3d, float u, float v, float w, f
         int wt[4];
         texunit_plane_weights(p ? c : 256 - c, a, b, wt);
         size_t zo = (size_t)(p ? z1 : z0) * sz;
-        const float *c00 = t->texels + 4 * (zo + y0 * sy + x0), *c01 = t->texels + 4 * (zo + y0 * sy + x1);
-        const float *c10 = t->texels + 4 * (zo + y1 * sy + x0), *c11 = t->texels + 4 * (zo + y1 * sy + x1);
+        const uint8_t *c00 = t->bytes + 4 * (zo + y0 * sy + x0), *c01 = t->bytes + 4 * (zo + y0 * sy + x1);
+        const uint8_t *c10 = t->bytes + 4 * (zo + y1 * sy + x0), *c11 = t->bytes + 4 * (zo + y1 * sy + x1);
         for (int ch = 0; ch < 4; ch++)
-            acc[ch] += wt[0] * (int)c00[ch] + wt[1] * (int)c01[ch] + wt[2] * (int)c10[ch] + wt[3] * (int)c11[ch];
+            acc[ch] += wt[0] * c00[ch] + wt[1] * c01[ch] + wt[2] * c10[ch] + wt[3] * c11[ch];
     }
     for (int ch = 0; ch < 4; ch++) out[ch] = texunit_unorm16(acc[ch]);
 }
@@ -261,6 +262,7 @@ static void sample3d(const ftex *t, int filter, float u, float v, float w, float
 struct om_scene {
     ftex placement, nightsky, curl, lowres, hires;
     float *store[5];
+    uint8_t *bstore[5];
     float cam[40];   /* UniformCameraObject, 160 B: Shader.h:24-29 */
     float sun[29];   /* UniformSunObject,    116 B: SkyManager.h:8-14 */
     float sky[13];   /* UniformSkyObject,     52 B: SkyManager.h:28-36 */
@@ -283,7 +285,7 @@ om_scene *om_scene_create(void) {
 }
 void om_scene_destroy(om_scene *s) {
     if (!s) return;
-    for (int i = 0; i < 5; i++) free(s->store[i]);
+    for (int i = 0; i < 5; i++) { free(s->store[i]); free(s->bstore[i]); }
     free(s);
 }
 int om_scene_set_texture(om_scene *s, int slot, const uint8_t *rgba8, int w, int h, int d) {
@@ -292,9 +294,12 @@ int om_scene_set_texture(om_scene *s, int slot, const uint8_t *rgba8, int w, int
     float *f = (float *)malloc(n * sizeof(float));
     if (!f) return -2;
     for (size_t i = 0; i < n; i++) f[i] = (float)rgba8[i];             /* integer texel values; normalised after filtering */
-    free(s->store[slot]);
-    s->store[slot] = f;
-    ftex t = {f, w, h, d};
+    uint8_t *bcopy = (uint8_t *)malloc(n);
+    if (!bcopy) { free(f); return -2; }
+    memcpy(bcopy, rgba8, n);
+    free(s->store[slot]); free(s->bstore[slot]);
+    s->store[slot] = f; s->bstore[slot] = bcopy;
+    ftex t = {f, w, h, d, bcopy};
     switch (slot) {
         case OM_TEX_PLACEMENT: s->placement = t; break;
         case OM_TEX_NIGHTSKY:  s->nightsky = t; break;
