@@ -431,9 +431,12 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     // on several GPUs).  Scheduling only: every variant produces the same bits.
     int lanes = ctx->lanes_per_ray;
     if (lanes == 0) {
+        // measured (tools/shard_probe3.py, tools/variant_bench.sh): one lane per ray wins from ~3 waves up (4 for the sparser,
+        // less coherent rays of a phase dispatch); two lanes win down to under one wave (1080p phase dispatch: 0.45 -> 0.28 ms,
+        // 1/8 of a 1080p frame: 0.43 -> 0.33 ms); four and eight only pay for launches far below one wave
         double waves = (double)p.grid_w * (double)p.owned_rows / (148.0 * 1024.0);
-        lanes = 1;
-        while (lanes < 8 && waves * lanes < MM_SPLIT_WAVES) lanes *= 2;
+        double full = (mode == MM_PHASE16) ? 4.0 : MM_SPLIT_WAVES;
+        lanes = waves >= full ? 1 : waves >= 0.75 ? 2 : waves >= 0.3 ? 4 : 8;
     }
     int block_w, block_h;
     march_block_shape(lanes, &block_w, &block_h);
