@@ -128,6 +128,15 @@ MM_API int mm_dispatch_reproject(mm_ctx *ctx, void *stream);
 MM_API int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, const void *sky52,
                              int mode, float *out_host_rgba32f);
 
+/* ---- host frame for several GPUs (new; the end-to-end path of a sharded frame).  A packed w*h RGBA32F frame in HOST memory that
+ * is page-locked and mapped into this context's device (mm_host_register on memory the caller owns -- e.g. a POSIX shared-memory
+ * mapping that every rank's process opens -- or cudaHostAlloc).  Once bound, every mm_dispatch stores each finished pixel to
+ * the device image AND to this frame over PCIe, so the device->host transfer of an N-GPU frame runs on N links in parallel and
+ * overlaps the march; the frame is complete when every rank's stream has drained.  NULL unbinds. */
+MM_API int mm_host_register(mm_ctx *ctx, void *host, size_t bytes);
+MM_API int mm_host_unregister(mm_ctx *ctx, void *host);
+MM_API int mm_bind_host_mirror(mm_ctx *ctx, float *host_rgba32f_packed);
+
 /* ---- HDR -> RGBA8 (tonemap.frag:11-28, vignette omitted) of the bound output; device or host dst */
 MM_API int mm_tonemap_rgba8(mm_ctx *ctx, uint8_t *dst, int dst_is_device, void *stream);
 

@@ -70,6 +70,9 @@ def load_library():
         "mm_dispatch_reproject": (i32, [vp, vp]),
         "mm_render_to_host": (i32, [vp, vp, vp, vp, i32, vp]),
         "mm_tonemap_rgba8": (i32, [vp, vp, i32, vp]),
+        "mm_host_register": (i32, [vp, vp, sz]),
+        "mm_host_unregister": (i32, [vp, vp]),
+        "mm_bind_host_mirror": (i32, [vp, vp]),
         "mm_god_ray": (i32, [vp, vp, vp, vp, sz, vp, sz, i32, i32, vp]),
         "mm_radial_blur": (i32, [vp, vp, vp, vp, sz, vp, sz, i32, i32, vp]),
         "mm_tonemap_present": (i32, [vp, vp, sz, vp, sz, i32, i32, i32, vp]),

@@ -49,6 +49,7 @@ struct mm_ctx {
     cudaMipmappedArray_t ext_mip = nullptr;
     cudaSurfaceObject_t surf = 0;
     float *mirror = nullptr;       // set only for the duration of one mm_render_to_host dispatch
+    float *host_mirror = nullptr;  // mm_bind_host_mirror: device view of a page-locked host frame every dispatch also stores into
     uint32_t *counters = nullptr;
     bool counters_on = false;
     int filter = FILTER_HW;        // production default: texture-unit filtering (parity: the oracle's texture-unit model)
@@ -412,7 +413,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         p.tex[i].pow2 = is_pow2(s.w) && is_pow2(s.h) && is_pow2(s.d);
     }
     p.out = ctx->out; p.pitch = ctx->pitch; p.surf = ctx->surf;
-    p.mirror = ctx->mirror; p.mirror_pitch = (size_t)ctx->W * 16;
+    p.mirror = ctx->mirror ? ctx->mirror : ctx->host_mirror; p.mirror_pitch = (size_t)ctx->W * 16;
     p.counters = ctx->counters_on ? ctx->counters : nullptr;
     p.W = ctx->W; p.H = ctx->H; p.mode = mode;
     p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block;
@@ -527,6 +528,36 @@ int mm_render_to_host(mm_ctx *ctx, const void *camera160, const void *sun116, co
     if (!mapped)
         CU(cudaMemcpy2DAsync(out_host, (size_t)ctx->W * 16, ctx->out, ctx->pitch, (size_t)ctx->W * 16, ctx->H, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return MM_OK;
+}
+
+// ---- host frame shared by several processes (multi-GPU end-to-end path) -----------------------------------------
+int mm_host_register(mm_ctx *ctx, void *host, size_t bytes) {
+    if (!ctx || !host || bytes == 0) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaHostRegister(host, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return MM_OK;
+}
+
+int mm_host_unregister(mm_ctx *ctx, void *host) {
+    if (!ctx || !host) return MM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->host_mirror) { CU(cudaStreamSynchronize(ctx->stream)); ctx->host_mirror = nullptr; }
+    CU(cudaHostUnregister(host));
+    return MM_OK;
+}
+
+int mm_bind_host_mirror(mm_ctx *ctx, float *host_rgba32f) {
+    if (!ctx) return MM_ERR_ARG;
+    if (!host_rgba32f) { ctx->host_mirror = nullptr; return MM_OK; }
+    if (!ctx->out) return fail(ctx, MM_ERR_STATE, "mm_bind_host_mirror: bind the device output image first");
+    CU(cudaSetDevice(ctx->device));
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host_rgba32f) != cudaSuccess || attr.type != cudaMemoryTypeHost || !attr.devicePointer) {
+        cudaGetLastError();
+        return fail(ctx, MM_ERR_ARG, "mm_bind_host_mirror: the frame must be page-locked and mapped (cudaHostAlloc / mm_host_register)");
+    }
+    ctx->host_mirror = static_cast<float *>(attr.devicePointer);
     return MM_OK;
 }
 

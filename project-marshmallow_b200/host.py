@@ -120,6 +120,16 @@ class ComputeShader:
         self._check(self._lib.mm_bind_output_linear(self._ctx, C.c_void_p(int(device_ptr)), pitch, self.width, self.height))
         self.out_ptr, self.out_pitch = int(device_ptr), pitch
 
+    # ---- host frame shared by several ranks: every dispatch also stores its pixels there (D2H fused into the kernel)
+    def hostRegister(self, array):
+        self._check(self._lib.mm_host_register(self._ctx, _ptr(array), array.nbytes))
+
+    def hostUnregister(self, array):
+        self._check(self._lib.mm_host_unregister(self._ctx, _ptr(array)))
+
+    def bindHostMirror(self, array_or_none):
+        self._check(self._lib.mm_bind_host_mirror(self._ctx, _ptr(array_or_none) if array_or_none is not None else None))
+
     # ---- multi-GPU: CUDA-IPC export / import of the output image
     def allocDevice(self, nbytes):
         p = C.c_void_p()

@@ -58,6 +58,46 @@ class SharedFrame:
             self.remote_ptr = None
 
 
+class SharedHostFrame:
+    """The HOST copy of a sharded frame: one POSIX shared-memory mapping opened by every rank's process, page-locked and
+    mapped into each rank's GPU.  Every rank's march kernel stores its pixels there as it finishes them (next to the store
+    into rank 0's device image), so the device->host transfer of the frame runs over N PCIe links in parallel and overlaps
+    the march; after a barrier the frame is complete in `self.array` on every rank -- no gather, no copy."""
+
+    def __init__(self, cs, rank, world, dist=None):
+        import mmap
+        import os
+        self.cs, self.rank = cs, rank
+        nbytes = cs.width * cs.height * 16
+        name = [f"/dev/shm/marshmallow_frame_{os.getpid()}" if rank == 0 else None]
+        if rank == 0:
+            with open(name[0], "wb") as f:
+                f.truncate(nbytes)
+        if world > 1:
+            dist.broadcast_object_list(name, src=0)
+        self.path = name[0]
+        self._f = open(self.path, "r+b")
+        self._map = mmap.mmap(self._f.fileno(), nbytes)
+        self.array = np.frombuffer(self._map, dtype=np.float32).reshape(cs.height, cs.width, 4)
+        cs.hostRegister(self.array)
+        cs.bindHostMirror(self.array)
+        if world > 1:
+            dist.barrier()                    # every rank has the file open: rank 0 may unlink the name now
+        if rank == 0:
+            os.unlink(self.path)
+
+    def close(self):
+        if self.array is not None:
+            self.cs.bindHostMirror(None)
+            self.cs.hostUnregister(self.array)
+            self.array = None
+            try:
+                self._map.close()
+            except BufferError:           # a caller still holds a view of the frame; the mapping goes with its last reference
+                pass
+            self._f.close()
+
+
 class FrameRing:
     """Frame-parallel animation (BASELINE config 5): frame k is rendered whole by rank k % world.  Rank 0 owns one
     image slot per rank; every rank binds ITS slot (mapped through CUDA IPC on ranks != 0) and stores finished frames

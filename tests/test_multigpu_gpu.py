@@ -31,8 +31,19 @@ WORKER = textwrap.dedent("""
     cs.dispatch(mm.MM_FULL, rank, world, 4)
     cs.synchronize()
     dist.barrier()
+    # the same frame again with the shared HOST frame bound: every rank's kernel also stores its pixels into one
+    # page-locked shared-memory mapping (the end-to-end path: no gather, no device->host copy afterwards)
+    host = mm.multigpu.SharedHostFrame(cs, rank, world, dist)
+    if rank == 0: host.array[...] = -7.0
+    dist.barrier()
+    cs.dispatch(mm.MM_FULL, rank, world, 8)
+    cs.synchronize()
+    dist.barrier()
+    host_frame = host.array.copy() if rank == 0 else None
+    host.close()
     if rank == 0:
         sharded = cs.readOutput()
+        assert np.array_equal(host_frame.view(np.uint32), sharded.view(np.uint32)), "host frame differs from rank 0's device image"
         cs.allocOutput()
         cs.dispatch(mm.MM_FULL)
         cs.synchronize()
