@@ -386,6 +386,11 @@ def test_bad_arguments_are_rejected_on_gpu(mm, assets):
         cs.uploadTexture(mm.MM_TEX_LOWRES, assets["placement"])      # a 2D texture into a 3D sampler slot
     with pytest.raises(mm.MarshmallowError):
         cs.setFilterMode(9)
+    for bad_lanes in (3, 16, -1):
+        with pytest.raises(mm.MarshmallowError):
+            cs.setLanesPerRay(bad_lanes)
+    with pytest.raises(mm.MarshmallowError):
+        cs.bindHostMirror(np.zeros((36, 64, 4), np.float32))          # pageable host memory cannot be a kernel-side mirror
     cs.dispatch()                                                     # still usable after the errors
     cs.synchronize()
     cs.close()
@@ -406,3 +411,62 @@ def test_render_to_host_pinned_and_pageable_agree(mm, assets):
     cs.close()
     assert np.array_equal(pinned.view(np.uint32), pageable.view(np.uint32))
     assert np.array_equal(pinned.view(np.uint32), device.view(np.uint32))
+
+
+def test_bound_host_mirror_receives_every_dispatch(mm, assets):
+    """mm_bind_host_mirror: every dispatch also stores its pixels into a page-locked host frame (what each rank of a sharded
+    frame does with the shared host frame); the host frame equals the device image bit for bit, for full and partial dispatches."""
+    import torch
+    W, H = 203, 117
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+    cs.allocOutput()
+    cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+    pinned = torch.full((H, W, 4), -7.0, dtype=torch.float32).pin_memory()
+    cs.bindHostMirror(pinned.numpy())
+    cs.dispatch(mm.MM_FULL, 1, 3, 8)                   # one rank's share of a 3-way sharded frame
+    cs.synchronize()
+    part = pinned.numpy().copy()
+    rows = mm.multigpu.owned_rows(H, 1, 3, 8)
+    other = np.setdiff1d(np.arange(H), rows)
+    assert (part[other] == -7.0).all() and (part[rows] != -7.0).any(axis=-1).all()
+    cs.dispatch(mm.MM_FULL)
+    cs.synchronize()
+    assert np.array_equal(pinned.numpy().view(np.uint32), cs.readOutput().view(np.uint32))
+    cs.bindHostMirror(None)
+    pinned.fill_(-7.0)
+    cs.dispatch(mm.MM_FULL)
+    cs.synchronize()
+    assert (pinned.numpy() == -7.0).all()              # unbound: the host frame is left alone
+    cs.close()
+
+
+def test_randomised_scenes_match_their_oracles(mm, oracle, assets):
+    """Seeded random cameras, suns (day and night), times, winds and placements, small frames: the default mode against the
+    texture-unit-model oracle and the FP32 mode against the binary32 oracle -- counters and alpha bit for bit."""
+    rng = np.random.default_rng(2024)
+    night_map = scenes.synthetic_night_sky()
+    for i in range(12):
+        over = dict(yaw=float(rng.uniform(-np.pi, np.pi)), pitch=float(-rng.uniform(0.02, 1.2)), elevation=float(rng.uniform(0.0, 1.0)),
+                    azimuth=float(rng.uniform(0.0, 1.0)), time=float(rng.uniform(0, 500)),
+                    wind=tuple(float(x) for x in rng.uniform(-1.5, 1.5, 3)), pos=tuple(float(x) for x in rng.uniform(-500, 500, 3)))
+        if i % 3 == 2:
+            over["placement"] = (int(rng.integers(40, 255)), int(rng.integers(0, 256)))
+        W, H = int(rng.integers(40, 140)), int(rng.integers(24, 80))
+        sc = scenes.make_scene(mm, "C1", assets, W=W, H=H, **over)
+        night = night_map if sc["sun"][5] < 0 else None
+        for mode in ("hw", "exact"):
+            kfilter, ofilter = getattr(mm, _FILTERS[mode][0]), getattr(oracle, _FILTERS[mode][1])
+            ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=ofilter, nightsky=night).march(W, H)
+            cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                                  lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"], nightSky=night)
+            cs.allocOutput()
+            cs.enableCounters(True)
+            cs.setFilterMode(kfilter)
+            cs.setLanesPerRay(int(rng.choice([0, 1, 2, 4, 8])))
+            img = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+            cnt = cs.readCounters()
+            cs.close()
+            rep = oracle.parity_report(ref, img, rcnt, cnt)
+            assert rep["counter_mismatch_pixels"] == 0 and rep["alpha_identical_frac"] == 1.0 and rep["max_abs_diff_8bit"] <= 1, (i, mode, over, rep)

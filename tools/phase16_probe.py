@@ -1,4 +1,4 @@
-"""One MM_FULL frame then MM_PHASE16 dispatches at 1080p (for ncu: the small-launch regime).  argv[1] = trips in flight"""
+"""One MM_FULL frame then MM_PHASE16 dispatches at 1080p (for ncu: the small-launch regime).  argv[1] = lanes per ray"""
 import os, sys
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import numpy as np, torch, _pkg, scenes
