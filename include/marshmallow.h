@@ -44,8 +44,11 @@ enum mm_tex_slot {
 /* which pixels one dispatch marches */
 enum mm_dispatch_mode {
     MM_FULL = 0,            /* every pixel: the union of the reference's 16 phase dispatches */
-    MM_PHASE16 = 1          /* one reference dispatch: pixels (4*gx + o%4, 4*gy + o/4), o = int(sun.color.a)
+    MM_PHASE16 = 1,         /* one reference dispatch: pixels (4*gx + o%4, 4*gy + o/4), o = int(sun.color.a)
                                (compute-clouds.comp:291-301, VulkanApplication.cpp:1067-1071) */
+    MM_ROWS_SNAKE = 0x100   /* flag, OR-ed to a mode: the row-cyclic partition runs boustrophedon -- round k of the assignment
+                               hands its row_stride blocks out in rank order for even k and in reverse rank order for odd k,
+                               which cancels the systematic cost gradient between ranks (rows nearer the horizon cost more) */
 };
 
 /* sampler arithmetic (see DESIGN.md "sampler modes").  Vulkan leaves linear-filter precision to the implementation;

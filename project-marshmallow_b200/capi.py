@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(HERE, "..", "include", "marshmallow.h")
 
 MM_FULL, MM_PHASE16 = 0, 1
+MM_ROWS_SNAKE = 0x100
 MM_FILTER_EXACT, MM_FILTER_HW, MM_FILTER_HYBRID = 0, 1, 2
 MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES = range(5)
 

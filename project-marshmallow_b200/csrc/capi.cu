@@ -374,7 +374,7 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
     for (int b = 0; b < nblockrows; b++) {
         int j = b * block_h + block_h / 2, py;
         if (p.mode == DISPATCH_PHASE16) py = j * 4;
-        else { int k = j / p.row_block; py = (p.row_begin + k * p.row_stride) * p.row_block + (j - k * p.row_block); }
+        else { int k = j / p.row_block; py = owned_block(k, p.row_begin, p.row_stride, p.row_snake) * p.row_block + (j - k * p.row_block); }
         if (py >= p.H) py = p.H - 1;
         double spy = 2.0 * py / p.H - 1.0;
         double tanH = cam[37];
@@ -390,8 +390,10 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
 
 int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream_v) {
     if (!ctx) return MM_ERR_ARG;
+    const int snake = (mode & MM_ROWS_SNAKE) ? 1 : 0;
+    mode &= ~MM_ROWS_SNAKE;
     if (mode != MM_FULL && mode != MM_PHASE16) return fail(ctx, MM_ERR_ARG, "mm_dispatch: unknown mode %d", mode);
-    if (row_begin < 0 || row_stride <= 0 || row_block <= 0) return fail(ctx, MM_ERR_ARG, "mm_dispatch: bad row partition (%d,%d,%d)", row_begin, row_stride, row_block);
+    if (row_begin < 0 || row_stride <= 0 || row_block <= 0 || (snake && row_begin >= row_stride)) return fail(ctx, MM_ERR_ARG, "mm_dispatch: bad row partition (%d,%d,%d)", row_begin, row_stride, row_block);
     if (!ctx->have_uniforms) return fail(ctx, MM_ERR_STATE, "mm_dispatch: uniforms were never set");
     if (!ctx->out && !ctx->surf) return fail(ctx, MM_ERR_STATE, "mm_dispatch: no output image bound");
     static const int need[4] = {MM_TEX_PLACEMENT, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES};
@@ -416,10 +418,11 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     p.mirror = ctx->mirror ? ctx->mirror : ctx->host_mirror; p.mirror_pitch = (size_t)ctx->W * 16;
     p.counters = ctx->counters_on ? ctx->counters : nullptr;
     p.W = ctx->W; p.H = ctx->H; p.mode = mode;
-    p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block;
+    p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block; p.row_snake = snake;
     if (mode == MM_FULL) {
         int nblocks = (ctx->H + row_block - 1) / row_block;
-        int owned = row_begin < nblocks ? (nblocks - row_begin + row_stride - 1) / row_stride : 0;
+        int owned = 0;                                      // blocks k = 0, 1, ... of this partition that exist in the image
+        while (owned_block(owned, row_begin, row_stride, snake) < nblocks) owned++;
         p.owned_rows = owned * row_block;
         p.grid_w = ctx->W;
     } else {

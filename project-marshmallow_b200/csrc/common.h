@@ -21,6 +21,14 @@ struct TexDev {
 enum { TEX_PLACEMENT = 0, TEX_NIGHTSKY = 1, TEX_CURL = 2, TEX_LOWRES = 3, TEX_HIRES = 4, TEX_COUNT = 5 };
 enum { FILTER_EXACT = 0, FILTER_HW = 1, FILTER_HYBRID = 2 };
 enum { DISPATCH_FULL = 0, DISPATCH_PHASE16 = 1 };
+// row block index of the k-th block owned by partition `begin` of `stride` (cyclic, or boustrophedon when snake)
+__host__ __device__ inline int owned_block(int k, int begin, int stride, int snake) {
+    return k * stride + ((snake && (k & 1)) ? (stride - 1 - begin) : begin);
+}
+__host__ __device__ inline bool owns_block(int blk, int begin, int stride, int snake) {
+    int k = blk / stride, m = blk - k * stride;
+    return ((snake && (k & 1)) ? (stride - 1 - m) : m) == begin;
+}
 
 // Pixel tile of one warp: MM_TILE_W x (32 / MM_TILE_W); a block is MM_WARPS_X x MM_WARPS_Y warps.
 #ifndef MM_TILE_W
@@ -50,6 +58,7 @@ struct MarchParams {
     int W, H;
     int mode;                    // DISPATCH_*
     int row_begin, row_stride, row_block;
+    int row_snake;               // odd rounds of the row-cyclic assignment run in reverse rank order (MM_ROWS_SNAKE)
     int owned_rows;              // rows this dispatch enumerates (FULL), virtual rows (PHASE16)
     int grid_w;                  // pixel columns enumerated (W, or ceil(W/4) in PHASE16)
     // Execution order of the BLOCK_H-row block rows, most expensive first (rays nearest the horizon cross the longest

@@ -10,19 +10,26 @@ plumbing that carries the 64-byte handle and the barriers.
 import numpy as np
 
 
-def owned_rows(H, rank, world, row_block):
-    """Rows marched by `rank` -- the same enumeration as the kernel (csrc/cloud_march.cu) and mm_dispatch."""
+def owned_rows(H, rank, world, row_block, snake=False):
+    """Rows marched by `rank` -- the same enumeration as the kernel (csrc/common.h: owned_block) and mm_dispatch.
+    snake (MM_ROWS_SNAKE): odd rounds of the cyclic assignment run in reverse rank order, so no rank is systematically
+    nearer the (expensive) horizon inside every round."""
     rows = []
     nblocks = (H + row_block - 1) // row_block
-    for b in range(rank, nblocks, world):
+    k = 0
+    while True:
+        b = k * world + ((world - 1 - rank) if (snake and k % 2) else rank)
+        if b >= nblocks:
+            break
         rows.extend(y for y in range(b * row_block, min(H, (b + 1) * row_block)))
+        k += 1
     return np.asarray(rows, dtype=np.int64)
 
 
-def partition_is_exact_cover(H, world, row_block):
+def partition_is_exact_cover(H, world, row_block, snake=False):
     seen = np.zeros(H, np.int32)
     for r in range(world):
-        seen[owned_rows(H, r, world, row_block)] += 1
+        seen[owned_rows(H, r, world, row_block, snake)] += 1
     return bool((seen == 1).all())
 
 

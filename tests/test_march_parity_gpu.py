@@ -215,8 +215,18 @@ def test_row_partition_union_equals_full_frame(mm, assets):
             cs.dispatch(mm.MM_FULL, r, n, block)
         cs.synchronize()
         img = t.cpu().numpy()
-        cs.close()
         assert np.array_equal(img.view(np.uint32), full.view(np.uint32)), (n, block)
+        # the boustrophedon order of the same partition (MM_ROWS_SNAKE): each rank writes exactly owned_rows(..., snake=True)
+        t.fill_(-7.0)
+        for r in range(n):
+            cs.dispatch(mm.MM_FULL | mm.MM_ROWS_SNAKE, r, n, block)
+            cs.synchronize()
+            if r == 0:
+                rows = np.nonzero((t.cpu().numpy() != -7.0).any(axis=(1, 2)))[0]
+                assert np.array_equal(rows, mm.multigpu.owned_rows(H, 0, n, block, snake=True)), (n, block)
+        img = t.cpu().numpy()
+        cs.close()
+        assert np.array_equal(img.view(np.uint32), full.view(np.uint32)), (n, block, "snake")
 
 
 def test_render_to_host_end_to_end(mm, oracle, assets):

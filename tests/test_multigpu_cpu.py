@@ -16,6 +16,7 @@ def test_partition_is_an_exact_cover(mm):
         for world in (1, 2, 3, 8):
             for block in (1, 2, 4, 16):
                 assert mm.multigpu.partition_is_exact_cover(H, world, block), (H, world, block)
+                assert mm.multigpu.partition_is_exact_cover(H, world, block, snake=True), (H, world, block, "snake")
 
 
 def test_partition_matches_oracle_dispatch(mm, oracle, assets):
@@ -45,6 +46,20 @@ def test_row_cyclic_balances_load_better_than_bands(mm, oracle, assets):
     assert eff(cyc) > 0.85 and eff(cyc) > eff(band) + 0.2
 
 
+def test_snake_order_removes_the_rank_bias_of_coarse_row_blocks(mm, oracle, assets):
+    """With 8-row blocks (the kernels' tile height) the plain cyclic order gives the last rank of every round the rows nearest
+    the horizon; running odd rounds in reverse rank order (MM_ROWS_SNAKE) cancels that gradient."""
+    import scenes
+    W, H = 240, 540                     # 4K's row count / 4: 8 ranks x 8 rows = 64-row rounds, as on the real frame
+    sc = scenes.make_scene(mm, "C3", assets, W=W, H=H)
+    _, cnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"]).march(W, H)
+    row_cost = (cnt[..., 1] + 2 * cnt[..., 2]).sum(axis=1).astype(np.float64)
+    eff = lambda parts: np.mean(parts) / np.max(parts)
+    plain = [row_cost[mm.multigpu.owned_rows(H, r, 8, 8)].sum() for r in range(8)]
+    snake = [row_cost[mm.multigpu.owned_rows(H, r, 8, 8, snake=True)].sum() for r in range(8)]
+    assert eff(snake) > eff(plain) and eff(snake) > 0.93, (eff(plain), eff(snake))
+
+
 WORKER = textwrap.dedent("""
     import os, sys
     sys.path.insert(0, {root!r})
@@ -56,10 +71,11 @@ WORKER = textwrap.dedent("""
     handle = bytes(range(64)) if rank == 0 else None
     got = mm.multigpu.exchange_handle(handle, rank, 2, dist)
     assert got == bytes(range(64)), got
-    rows = mm.multigpu.owned_rows(37, rank, 2, 2)
-    gathered = [None, None]
-    dist.all_gather_object(gathered, rows.tolist())
-    assert sorted(gathered[0] + gathered[1]) == list(range(37))
+    for snake in (False, True):
+        rows = mm.multigpu.owned_rows(37, rank, 2, 2, snake)
+        gathered = [None, None]
+        dist.all_gather_object(gathered, rows.tolist())
+        assert sorted(gathered[0] + gathered[1]) == list(range(37))
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")

@@ -36,7 +36,7 @@ WORKER = textwrap.dedent("""
     host = mm.multigpu.SharedHostFrame(cs, rank, world, dist)
     if rank == 0: host.array[...] = -7.0
     dist.barrier()
-    cs.dispatch(mm.MM_FULL, rank, world, 8)
+    cs.dispatch(mm.MM_FULL | mm.MM_ROWS_SNAKE, rank, world, 8)
     cs.synchronize()
     dist.barrier()
     host_frame = host.array.copy() if rank == 0 else None

@@ -1,21 +1,22 @@
-"""Per-rank shard times on one GPU: N x row_block x lanes grid.  usage: shard_probe3.py [config]"""
+"""Per-rank shard times on one GPU: N x row_block x lanes grid.  usage: shard_probe3.py [config] [--snake]"""
 import os, sys
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import numpy as np, torch, _pkg, scenes
 mm = _pkg.load_package()
 assets = scenes.load_assets()
-cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
+cfg = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "C2"
 sc = scenes.make_scene(mm, cfg, assets)
 W, H = sc["W"], sc["H"]
 cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"], lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
 cs.allocOutput()
 cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+SNAKE = mm.MM_ROWS_SNAKE if "--snake" in sys.argv else 0
 def t(r, n, rb):
     best = 1e9
     for rep in range(3):
         flush.fill_(1); torch.cuda.synchronize()
-        cs.dispatch(mm.MM_FULL, r, n, rb)
+        cs.dispatch(mm.MM_FULL | SNAKE, r, n, rb)
         v = cs.lastKernelMs()
         if rep: best = min(best, v)
     return best
