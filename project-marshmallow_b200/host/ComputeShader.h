@@ -7,6 +7,10 @@
 //   updateUniformBuffers(cam, camPrev, sky, sun)                updateUniformBuffers(cam, camPrev, sky, sun)   (same order)
 //   bindShader(cmdBuf) + vkCmdDispatch + vkQueueSubmit          dispatch(mode, stream)
 //   cleanupUniforms() / ~Shader                                 ~ComputeShader
+//   ReprojectShader (Shader.h:380-452)                          bindPrevious + dispatchReproject
+//   PostProcessShader x3 (Shader.h:460-520): god-ray.frag,      godRay / radialBlur / tonemapPresent, or postChain (fused)
+//       radialBlur.frag, tonemap.frag
+//   the shadow march inside model.frag:240-283                  cloudShadow(positions)
 // Errors throw std::runtime_error, as every Vulkan failure does in the reference (caught in main.cpp:8-14).
 // Header-only; link against libmarshmallow_b200.so.
 #pragma once
@@ -65,6 +69,36 @@ public:
     void bindOutputExternalFd(int opaqueFd, size_t allocBytes) { check(mm_bind_output_external_fd(ctx_, opaqueFd, allocBytes, extent_.width, extent_.height)); }
 
     void setFilterMode(int mode) { check(mm_set_filter_mode(ctx_, mode)); }
+    void setLanesPerRay(int lanes) { check(mm_set_lanes_per_ray(ctx_, lanes)); }     // scheduling only; 0 = per dispatch
+
+    // ReprojectShader: previous image (descriptor set 1) -> bound output, then dispatch(MM_PHASE16) re-marches 1/16 of it
+    void bindPrevious(const float *devicePtr, size_t pitchBytes) { check(mm_bind_previous_linear(ctx_, devicePtr, pitchBytes)); }
+    void dispatchReproject(void *cudaStream = nullptr) { check(mm_dispatch_reproject(ctx_, cudaStream)); }
+
+    // PostProcessShader x3 (VulkanApplication.cpp:943-968, 1016); device images, source != destination
+    void godRay(const UniformCameraObject &cam, const UniformSunObject &sun, const float *src, float *dst, void *cudaStream = nullptr) {
+        check(mm_god_ray(ctx_, &cam, &sun, src, pitch_, dst, pitch_, extent_.width, extent_.height, cudaStream));
+    }
+    void radialBlur(const UniformCameraObject &cam, const UniformSunObject &sun, const float *src, float *dst, void *cudaStream = nullptr) {
+        check(mm_radial_blur(ctx_, &cam, &sun, src, pitch_, dst, pitch_, extent_.width, extent_.height, cudaStream));
+    }
+    void tonemapPresent(const float *src, uint8_t *dst8888, bool bgra = true, void *cudaStream = nullptr) {
+        check(mm_tonemap_present(ctx_, src, pitch_, dst8888, (size_t)extent_.width * 4, extent_.width, extent_.height, bgra ? 1 : 0, cudaStream));
+    }
+    // the whole chain on the bound cloud image: god rays -> radial blur -> tone map + vignette -> swapchain bytes
+    void postChain(const UniformCameraObject &cam, const UniformSunObject &sun, uint8_t *dst8888, bool bgra = true, void *cudaStream = nullptr) {
+        check(mm_post_chain(ctx_, &cam, &sun, image_, pitch_, dst8888, (size_t)extent_.width * 4, extent_.width, extent_.height, bgra ? 1 : 0, cudaStream));
+    }
+
+    // model.frag:240-283 for n world positions (host arrays): accumDensity per point; shade with 1 - 2*density (:281)
+    std::vector<float> cloudShadow(const float *positionsXYZ, int n) {
+        std::vector<float> out((size_t)n);
+        check(mm_cloud_shadow(ctx_, positionsXYZ, n, 0, out.data(), nullptr, nullptr));
+        return out;
+    }
+
+    // sharded frames: a page-locked host frame every dispatch also stores into (mm_host_register'ed or cudaHostAlloc'ed)
+    void bindHostMirror(float *hostFrame) { check(mm_bind_host_mirror(ctx_, hostFrame)); }
 
     // VulkanApplication.cpp:1062-1071 + 168-177.  mode MM_PHASE16 reproduces one reference dispatch.
     void dispatch(int mode = MM_FULL, void *cudaStream = nullptr, int rowBegin = 0, int rowStride = 1, int rowBlock = 1) {
