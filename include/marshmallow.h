@@ -114,6 +114,11 @@ MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
 MM_API int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
 MM_API int mm_synchronize(mm_ctx *ctx);
+/* host-only diagnostics (no device needed): the order in which mm_dispatch would execute the block rows (block_h rows of the
+ * partition's compact row index each) of such a dispatch, most expensive first; order_out needs ceil(owned_rows / block_h)
+ * entries (at most 4096).  The cost order is a scheduling hint and never changes results. */
+MM_API int mm_plan_block_rows(const void *camera160, int h, int mode, int row_begin, int row_stride, int row_block, int block_h,
+                              uint16_t *order_out, int *count_out);
 
 /* ---- reprojection pass: replaces the ReprojectShader dispatch that precedes the cloud dispatch in the engine's
  * frame (Shaders/reproject.comp; Shader.h:380-452; VulkanApplication.cpp:1053-1059).  Reads the PREVIOUS frame's

@@ -67,6 +67,7 @@ def load_library():
         "mm_set_lanes_per_ray": (i32, [vp, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
         "mm_synchronize": (i32, [vp]),
+        "mm_plan_block_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, C.POINTER(i32)]),
         "mm_bind_previous_linear": (i32, [vp, vp, sz]),
         "mm_dispatch_reproject": (i32, [vp, vp]),
         "mm_render_to_host": (i32, [vp, vp, vp, vp, i32, vp]),
@@ -116,6 +117,18 @@ def host_sky(elevation, azimuth, wind=(1.0, 0.05, 1.0), time=0.0, pixel_phase=0,
     if rc:
         raise MarshmallowError(rc, "mm_host_sky")
     return sun, sky
+
+
+def plan_block_rows(cam, H, mode=MM_FULL, row_begin=0, row_stride=1, row_block=1, block_h=8):
+    """Execution order of the block rows of a dispatch, most expensive first (host-only; mm_plan_block_rows)."""
+    lib = load_library()
+    cam = np.ascontiguousarray(cam, np.float32)
+    order = np.zeros(4096, np.uint16)
+    n = C.c_int()
+    rc = lib.mm_plan_block_rows(_ptr(cam), H, mode, row_begin, row_stride, row_block, block_h, _ptr(order), C.byref(n))
+    if rc:
+        raise MarshmallowError(rc, "mm_plan_block_rows")
+    return order[:n.value].copy()
 
 
 def host_camera(position, yaw, pitch, fov_deg=45.0, aspect=1920.0 / 1080.0):

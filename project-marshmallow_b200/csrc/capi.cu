@@ -400,6 +400,31 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
     for (int b = 0; b < nblockrows; b++) order[b] = keys[(dbg && dbg[0] == 'r') ? nblockrows - 1 - b : b].i;
 }
 
+// Host-only: the execution order mm_dispatch would give the block rows of a dispatch (most expensive first).  No device needed.
+int mm_plan_block_rows(const void *camera160, int h, int mode, int row_begin, int row_stride, int row_block, int block_h,
+                       uint16_t *order_out, int *count_out) {
+    if (!camera160 || !order_out || !count_out || h <= 0 || row_stride <= 0 || row_block <= 0 || block_h <= 0 || row_begin < 0) return MM_ERR_ARG;
+    const int snake = (mode & MM_ROWS_SNAKE) ? 1 : 0;
+    mode &= ~MM_ROWS_SNAKE;
+    if (mode != MM_FULL && mode != MM_PHASE16) return MM_ERR_ARG;
+    static thread_local MarchParams p;
+    memcpy(p.cam, camera160, sizeof p.cam);
+    p.H = h; p.mode = mode; p.row_begin = row_begin; p.row_stride = row_stride; p.row_block = row_block; p.row_snake = snake;
+    if (mode == MM_FULL) {
+        int nblocks = (h + row_block - 1) / row_block, owned = 0;
+        while (owned_block(owned, row_begin, row_stride, snake) < nblocks) owned++;
+        p.owned_rows = owned * row_block;
+    } else {
+        p.owned_rows = (h + 3) / 4;
+    }
+    int n = (p.owned_rows + block_h - 1) / block_h;
+    if (n > 4096) return MM_ERR_UNSUPPORTED;
+    order_block_rows(p, p.block_row_order, n, block_h);
+    memcpy(order_out, p.block_row_order, sizeof(uint16_t) * (size_t)n);
+    *count_out = n;
+    return MM_OK;
+}
+
 int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream_v) {
     if (!ctx) return MM_ERR_ARG;
     const int snake = (mode & MM_ROWS_SNAKE) ? 1 : 0;

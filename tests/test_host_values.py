@@ -52,3 +52,31 @@ def test_camera_block(mm):
     assert np.allclose(cam[32:36], [0, 1, 1, 1])
     assert cam[36] == pytest.approx(1920 / 1080) and cam[37] == pytest.approx(np.tan(0.5 * 0.01745 * 45), rel=1e-6)
     assert np.allclose(view[:3, 3], -R @ np.array([0, 1, 1]), atol=1e-6)
+
+
+def test_block_rows_run_most_expensive_first_and_the_horizon_row_is_not_mistaken_for_free(mm):
+    """mm_dispatch's cost order (host-only planner): rays just above the horizon are the longest of the frame, rows entirely
+    below it are free.  The block row that STRADDLES the horizon must run first -- judged by its middle ray it looked free and
+    ran last, which cost the rank owning it 15 % of its share of a 4K frame."""
+    import scenes
+    cfg = scenes.CONFIGS["C3"]
+    cam = mm.host_camera(cfg["pos"], cfg["yaw"], cfg["pitch"], 45.0, 1920.0 / 1080.0)
+    H = 2160
+
+    def elevation(py):
+        spy = 2.0 * py / H - 1.0
+        d = np.array([-cam[2] - spy * cam[37] * cam[1], -cam[6] - spy * cam[37] * cam[5], -cam[10] - spy * cam[37] * cam[9]], np.float64)
+        return d[1] / np.linalg.norm(d)
+    horizon = next(py for py in range(H) if elevation(py) < 0)            # first row below the horizon
+    for rank in range(8):
+        rows = mm.multigpu.owned_rows(H, rank, 8, 8)
+        order = mm.plan_block_rows(cam, H, mm.MM_FULL, rank, 8, 8, 8)
+        assert sorted(order.tolist()) == list(range(len(rows) // 8))
+        tops = np.array([rows[8 * b] for b in order])                     # first image row of each block row, in execution order
+        above = tops < horizon
+        assert above[: above.sum()].all(), "a block row with rays above the horizon was scheduled after a free one"
+        assert (np.diff(tops[: above.sum()]) < 0).all(), "above the horizon: nearest to the horizon (most expensive) first"
+    # rank 0 of 8 owns the straddling block row at 4K (rows 1536-1543 around the horizon row): it is the FIRST to run
+    rows0 = mm.multigpu.owned_rows(H, 0, 8, 8)
+    first = mm.plan_block_rows(cam, H, mm.MM_FULL, 0, 8, 8, 8)[0]
+    assert rows0[8 * first] < horizon <= rows0[8 * first + 7]
