@@ -76,6 +76,24 @@ WORKER = textwrap.dedent("""
         gathered = [None, None]
         dist.all_gather_object(gathered, rows.tolist())
         assert sorted(gathered[0] + gathered[1]) == list(range(37))
+    # the shared HOST frame of a sharded frame: one shared-memory mapping opened by both processes (the CUDA page-locking and
+    # the kernel-side stores are the GPU half, tests/test_multigpu_gpu.py); here every rank writes its own rows from the CPU
+    class FakePass:
+        width, height = 40, 37
+        def hostRegister(self, a): pass
+        def hostUnregister(self, a): pass
+        def bindHostMirror(self, a): pass
+    host = mm.multigpu.SharedHostFrame(FakePass(), rank, 2, dist)
+    assert host.array.shape == (37, 40, 4) and not os.path.exists(host.path)      # unlinked once every rank has it open
+    host.array[mm.multigpu.owned_rows(37, rank, 2, 8)] = float(rank + 1)
+    dist.barrier()
+    import numpy as np
+    want = np.zeros(37)
+    for r in range(2):
+        want[mm.multigpu.owned_rows(37, r, 2, 8)] = r + 1
+    assert (host.array[:, 0, 0] == want).all() and (host.array == host.array[:, :1, :1]).all()
+    dist.barrier()
+    host.close()
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
