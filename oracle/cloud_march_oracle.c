@@ -909,6 +909,13 @@ int om_sample(const om_scene *s, int slot, int filter, const float *uvw, int n, 
     return 0;
 }
 
+/* trampoline with the signature of glsl_env.h's sample_fn: lets the reference's own shader text, compiled by ref_cc_shim.cpp,
+ * fetch through this oracle's sampler (user -> {scene, filter mode}) */
+void om_sample_callback(void *user, int slot, const float *uvw, float *out_rgba) {
+    const om_sampler_ctx *c = (const om_sampler_ctx *)user;
+    om_sample(c->scene, slot, c->filter, uvw, 1, out_rgba);
+}
+
 /*
  * HDR -> RGBA8 map used by the parity gate: tonemap.frag:11-28 (Uncharted-2, exposure 0.7,
  * invGamma 1/2.2, white 50.2), vignette (:30-32) omitted; alpha = clamp(a,0,1).  round-half-up.

@@ -24,6 +24,8 @@ int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_s
 void om_set_window(int trips_per_window /* 1 = plain loop; >1 = windowed replay model of the kernel's ray-split mode */);
 void om_set_litmask_buffer(uint32_t *buf /* 8 x uint32 per pixel (zeroed by the caller), or NULL */);
 int om_sample(const om_scene *s, int slot, int filter, const float *uvw, int n, float *out_rgba);
+typedef struct { const om_scene *scene; int filter; } om_sampler_ctx;
+void om_sample_callback(void *user /* om_sampler_ctx* */, int slot, const float *uvw, float *out_rgba);
 void om_tonemap_rgba8(const float *rgba32f, size_t npix, uint8_t *rgba8);
 
 /* helper known-answer hooks (compute-clouds.comp:65-77,147-177,193-208) */
