@@ -8,11 +8,17 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this file's shared object.  The shipped library (csrc/) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned by the reference" for the march -- the reference has no tests,
- * golden frames or runnable build for this path in this environment (no Vulkan loader, glslang or
- * lavapipe).  The restatement is pinned only by (i) helper-level known
- * answers derived by hand from the GLSL (tests/test_oracle_helpers.py) and (ii) the quirk
- * register of SURVEY.md section 7 (Q1..Q14), each reproduced below and marked "Qn".
+ * PARITY STATUS: PINNED AGAINST THE REFERENCE'S OWN SHADER TEXT.  The reference has no tests or golden frames for this path and
+ * its shader cannot run on a Vulkan device here (no loader, glslang or lavapipe), but the shader SOURCE can
+ * run on the CPU: oracle/Makefile rewrites compute-clouds.comp (and model.frag for the shadow march below) lexically into C++
+ * (glsl_to_cpp.py) and compiles it inside the GLSL environment of glsl_env.h into oracle/_ref/ -- control flow, constants,
+ * argument and operator order are the reference's, the language (vector types, built-ins as defined below, texture() routed to
+ * this file's sampler) is the environment's.  tests/test_reference_shader.py: every channel of every pixel bit-identical and
+ * identical texture() call counts in 8 scenes (day, sunset, storm, wind, night; both samplers); the shadow march bit-identical
+ * for 8000 positions x 5 scenes.  What the reference cannot pin is the language itself -- GLSL leaves the precision of pow,
+ * of filtering and of contraction to the implementation -- so the definitions below remain this project's contract, and
+ * helper-level known answers (tests/test_oracle_helpers.py), the quirk register of SURVEY.md section 7 (Q1..Q14, marked "Qn"
+ * below) and committed golden frames guard them against drift.
  *
  * Arithmetic contract (what "bit-exact decision path" means for the CUDA kernel):
  *   - every expression is evaluated in IEEE binary32, in the order written in the GLSL, one

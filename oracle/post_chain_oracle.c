@@ -7,7 +7,9 @@
  * recorded back to back over three RGBA32F framebuffers in VulkanApplication.cpp:936-968 and :1016 (the first
  * pass, background.frag, is a texel-for-texel copy of the cloud image and is not restated).
  *
- * PARITY STATUS: "parity unpinned by the reference" (no tests or golden images; no Vulkan here).  Restated under the
+ * PARITY STATUS: pinned against the reference's own shader texts (god-ray.frag, radialBlur.frag, tonemap.frag rewritten lexically
+ * into C++ and run on the CPU, oracle/_ref/libref_passes.so): both RGBA32F framebuffers bit-identical, the UNORM8 present
+ * byte-identical (tests/test_reference_shader.py).  The reference has no tests or golden images of its own.  Restated under the
  * arithmetic contract of cloud_march_oracle.c: IEEE binary32, GLSL order, one rounding per operator, no contraction.
  * Fixed interpretations:
  *   - fragUV of the pixel (x, y) is ((x + 0.5)/W, (y + 0.5)/H): the quad's UVs (Geometry.cpp:94-99) interpolated at the

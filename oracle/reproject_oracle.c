@@ -10,7 +10,8 @@
  * where GLSL leaves freedom: round() = round half away from zero (roundf); ivec2(float) truncates, saturates at the
  * int32 range and sends NaN to 0 (what CUDA's cvt.rzi.s32.f32 does); a ray that misses the shell keeps
  * isect.point = vec3(0) exactly as reproject.comp:58-62 initialises it.
- * PARITY STATUS: unpinned by the reference (no tests / golden frames; the shader cannot be executed here).
+ * PARITY STATUS: pinned against the reference's own shader text -- reproject.comp rewritten lexically into C++ and run on the CPU
+ * (oracle/_ref/libref_passes.so, oracle/glsl_env.h): images bit-identical (tests/test_reference_shader.py).
  */
 #include <math.h>
 #include <stdint.h>

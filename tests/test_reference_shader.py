@@ -77,3 +77,85 @@ def test_the_deterministic_pow_only_moves_last_bits(mm, oracle, assets):
     got, _, _ = _run_reference_shader(oracle, S, oracle.OM_FILTER_FP32, sc, np.stack([xs // 4, ys // 4], 1))
     rep = oracle.parity_report(want[ys, xs][None], got[ys, xs][None])
     assert rep["frac_within_1"] > 0.995 and rep["alpha_identical_frac"] > 0.995, rep
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# The other restated shaders -- reproject.comp, god-ray.frag, radialBlur.frag, tonemap.frag and the shadow march inside model.frag
+# -- compiled the same way into oracle/_ref/libref_passes.so.
+REF_PASSES = os.path.join(os.path.dirname(REF_CC), "libref_passes.so")
+
+
+def _passes():
+    lib = C.CDLL(REF_PASSES)
+    vp, i32 = C.c_void_p, C.c_int
+    lib.ref_reproject.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.ref_god_ray.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.ref_radial_blur.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.ref_tonemap.argtypes = [vp, i32, i32, vp]
+    lib.ref_cloud_shadow.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    return lib
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PASSES), reason="oracle/_ref/libref_passes.so not built (reference tree absent)")
+@pytest.mark.parametrize("W,H", [(160, 90), (97, 61)])
+def test_reproject_oracle_equals_the_reference_shader_text(mm, oracle, W, H):
+    rng = np.random.default_rng(W)
+    src = (rng.random((H, W, 4)) * 20).astype(np.float32)
+    lib = _passes()
+    cams = [(mm.host_camera((0, 1, 1), -np.pi / 2, -20 * scenes.DEG2RAD), mm.host_camera((0, 1, 1), -np.pi / 2, -20 * scenes.DEG2RAD)),
+            (mm.host_camera((0, 1, 1), -np.pi / 2, -20 * scenes.DEG2RAD), mm.host_camera((3.0, 1.0, 2.0), -np.pi / 2 + 0.01, -19 * scenes.DEG2RAD)),
+            (mm.host_camera((5, 2, -3), 0.4, -0.6), mm.host_camera((4, 2, -3.5), 0.47, -0.55))]
+    for cam, prev in cams:
+        want = oracle.reproject(cam, prev, src)
+        got = np.empty_like(src)
+        assert lib.ref_reproject(oracle._p(cam), oracle._p(prev), oracle._p(src), W, H, oracle._p(got)) == 0
+        assert _same_bits(want, got)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PASSES), reason="oracle/_ref/libref_passes.so not built (reference tree absent)")
+@pytest.mark.parametrize("name,over", [("C1", {}), ("C3", {}), ("C1", dict(yaw=-1.2, pitch=-0.5)), ("C1", dict(elevation=0.75))])
+def test_post_chain_oracle_equals_the_reference_shader_texts(mm, oracle, assets, name, over):
+    W, H = 160, 90
+    sc = scenes.make_scene(mm, name, assets, W=W, H=H, **over)
+    night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
+    img, _ = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], nightsky=night).march(W, H, counters=False)
+    cam, sun = np.ascontiguousarray(sc["cam"], np.float32), np.ascontiguousarray(sc["sun"], np.float32)
+    lib = _passes()
+    fb1, fb2, fb3 = np.empty_like(img), np.empty_like(img), np.empty_like(img)
+    want1 = oracle.god_ray(cam, sun, img)
+    assert lib.ref_god_ray(oracle._p(cam), oracle._p(sun), oracle._p(img), W, H, oracle._p(fb1)) == 0
+    assert _same_bits(want1, fb1), "god-ray.frag"
+    want2 = oracle.radial_blur(cam, sun, want1)
+    assert lib.ref_radial_blur(oracle._p(cam), oracle._p(sun), oracle._p(want1), W, H, oracle._p(fb2)) == 0
+    assert _same_bits(want2, fb2), "radialBlur.frag"
+    want3 = oracle.tonemap_present(want2)
+    assert lib.ref_tonemap(oracle._p(want2), W, H, oracle._p(fb3)) == 0
+    quant = np.floor(255.0 * np.clip(np.nan_to_num(fb3, nan=0.0), 0.0, 1.0) + 0.5).astype(np.uint8)     # the swapchain's UNORM8 store
+    assert np.array_equal(quant, want3), "tonemap.frag"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PASSES), reason="oracle/_ref/libref_passes.so not built (reference tree absent)")
+@pytest.mark.parametrize("name,sampler,over", [("C1", "fp32", {}), ("C5", "texunit", {}), ("C3", "fp32", {}),
+                                               ("C1", "texunit", dict(time=60.0, wind=(0.7, 0.05, -1.3))), ("C1", "fp32", dict(pitch=0.3, yaw=0.4))])
+def test_cloud_shadow_oracle_equals_model_frag(mm, oracle, assets, name, sampler, over):
+    """model.frag's main() is run whole for every position; its accumDensity (which the shader only folds into the fragment colour) is
+    read back through a reference the rewrite puts in place of the variable's declaration (glsl_to_cpp.py --probe)."""
+    sc = scenes.make_scene(mm, name, assets, **over)
+    filt = oracle.OM_FILTER_TEXUNIT if sampler == "texunit" else oracle.OM_FILTER_FP32
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=filt, pow_mode=oracle.OM_POW_LIBM)
+    rng = np.random.default_rng(17)
+    pos = np.concatenate([rng.uniform(-50, 50, (4000, 3)), rng.uniform(-20000, 20000, (4000, 3)) * np.float32([1, 0.02, 1])]).astype(np.float32)
+    want, nf = S.cloud_shadow(pos, want_fetches=True)
+    got = np.empty(len(pos), np.float32)
+    fetches = (C.c_ulonglong * 2)()
+    ctx = _SamplerCtx(S.s, filt)
+    cam, sun, sky = (np.ascontiguousarray(sc[k], np.float32) for k in ("cam", "sun", "sky"))
+    assert _passes().ref_cloud_shadow(oracle._p(cam), oracle._p(sun), oracle._p(sky), C.cast(oracle.lib().om_sample_callback, C.c_void_p),
+                                      C.byref(ctx), oracle._p(pos), len(pos), oracle._p(got), fetches) == 0
+    assert _same_bits(want, got)
+    assert int(fetches[0]) + int(fetches[1]) == int(nf.sum())
+    assert (want > 0).mean() > 0.03
