@@ -84,7 +84,8 @@ WORKER = textwrap.dedent("""
         def hostUnregister(self, a): pass
         def bindHostMirror(self, a): pass
     host = mm.multigpu.SharedHostFrame(FakePass(), rank, 2, dist)
-    assert host.array.shape == (37, 40, 4) and not os.path.exists(host.path)      # unlinked once every rank has it open
+    assert host.array.shape == (37, 40, 4)
+    assert rank != 0 or not os.path.exists(host.path)      # rank 0 unlinks the name once every rank has the file open
     host.array[mm.multigpu.owned_rows(37, rank, 2, 8)] = float(rank + 1)
     dist.barrier()
     import numpy as np
