@@ -141,7 +141,7 @@ def run_reference(args):
         "config": {"workload": f"{args.config} {sc['W']}x{sc['H']} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
                    "filter": "oracle, texture-unit model sampler" if args.filter == "hw" else "oracle, binary32 sampler", "l2": "n/a (CPU)", "parallelism": f"{cores} host threads"},
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
-                         "note": "oracle port of compute-clouds.comp; stands in for the reference shader on lavapipe, which cannot run here"},
+                         "note": "oracle port of compute-clouds.comp (bit-identical to the reference's own shader text executed on the CPU, tests/test_reference_shader.py); stands in for the reference shader on lavapipe, which cannot run here"},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -404,7 +404,8 @@ def main():
                                              "warp_instructions_per_frame": winst[0], "source": os.path.relpath(prof, ROOT)}
             v = wq["pixels"] / wq["seconds"] / 1e6
             out["cpu_baseline"] = {"value": v, "unit": "Mpix/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"every {rows_step}th row of the same frame ({wq['pixels']} px), oracle port with counters, OpenMP"}
+                                   "sample": f"every {rows_step}th row of the same frame ({wq['pixels']} px), oracle port with counters, OpenMP",
+                                   "note": "the port is bit-identical to the reference's own shader text executed on the CPU (tests/test_reference_shader.py)"}
         print(json.dumps(out))
     if world > 1:
         torch.cuda.synchronize()
