@@ -1,5 +1,7 @@
 """Host-side value producers (mm_host_sky / mm_host_camera, CPU only) against hand-derived values of the
 reference formulas (SkyManager.cpp:15-70, camera.cpp:27-39,179-195, camera.h:72)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -80,3 +82,30 @@ def test_block_rows_run_most_expensive_first_and_the_horizon_row_is_not_mistaken
     rows0 = mm.multigpu.owned_rows(H, 0, 8, 8)
     first = mm.plan_block_rows(cam, H, mm.MM_FULL, 0, 8, 8, 8)[0]
     assert rows0[8 * first] < horizon <= rows0[8 * first + 7]
+
+
+REF_HOST = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_host.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HOST), reason="oracle/_ref/libref_host.so not built (reference tree absent)")
+def test_host_sky_equals_the_reference_skymanager(mm):
+    """mm_host_sky against the reference's OWN SkyManager.cpp, compiled verbatim from /root/reference (oracle/Makefile; a stub header
+    stands in for the Vulkan names SkyManager.h mentions): both uniform blocks byte for byte -- sun position, basis (incl. the
+    night-time negation), colour ramp, intensity, Rayleigh / Mie coefficients, wind and time -- over the app's own values and 2000
+    random (elevation, azimuth, wind, time, phase) tuples.  The reference never initialises its `turbidity` member; the shim
+    constructs the object on storage holding the intended value (oracle/ref_host_shim.cpp)."""
+    import ctypes as C
+    ref = C.CDLL(REF_HOST)
+    ref.ref_host_sky.argtypes = [C.c_float] * 3 + [C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(0)
+    cases = [(0.25, 0.25, (1, 0.05, 1), 0.0, 0), (0.008, 0.25, (1, 0.05, 1), 0.0, 3), (0.75, 0.25, (0.7, 0.05, -1.3), 123.5, 15),
+             (0.5, 0.5, (0, 0, 0), 1.0, 1), (0.0, 0.25, (1, 1, 1), 2.0, 2), (0.5, 0.25, (1, 0.05, 1), 0.0, 0)]
+    cases += [(float(rng.uniform(0, 1)), float(rng.uniform(0, 1)), tuple(float(x) for x in rng.uniform(-2, 2, 3)),
+               float(rng.uniform(0, 1000)), int(rng.integers(0, 16))) for _ in range(2000)]
+    for e, a, w, t, phase in cases:
+        for turbidity in (10.0, 3.5):
+            sun, sky = mm.host_sky(e, a, w, t, phase, turbidity)
+            rsun, rsky, wind = np.zeros(29, np.float32), np.zeros(13, np.float32), np.asarray(w, np.float32)
+            assert ref.ref_host_sky(e, a, turbidity, wind.ctypes.data, t, phase, rsun.ctypes.data, rsky.ctypes.data) == 0
+            assert np.array_equal(sun.view(np.uint32), rsun.view(np.uint32)), (e, a, sun, rsun)
+            assert np.array_equal(sky.view(np.uint32), rsky.view(np.uint32)), (e, a, sky, rsky)
