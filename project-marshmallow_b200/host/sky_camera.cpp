@@ -123,15 +123,22 @@ void Camera::updateFrame() {
 }
 
 void Camera::getView(float view[16]) const {
-    // rows of the rotation are right / up / forward; the camera looks along -forward
-    for (int c = 0; c < 3; c++) {
-        view[4 * c + 0] = m_right[c]; view[4 * c + 1] = m_up[c]; view[4 * c + 2] = m_forward[c]; view[4 * c + 3] = 0.0f;
-    }
-    for (int r = 0; r < 3; r++) {
-        const float *row = r == 0 ? m_right : (r == 1 ? m_up : m_forward);
-        view[12 + r] = row[0] * -m_position[0] + row[1] * -m_position[1] + row[2] * -m_position[2];
-    }
-    view[15] = 1.0f;
+    // camera.cpp:27-39: view = R * T as a 4x4 product in glm's order (column j of the result is
+    // ((R0*T[j][0] + R1*T[j][1]) + R2*T[j][2]) + R3*T[j][3]); rows of R are right / up / forward, the camera looks along -forward.
+    // Written out as the product, not in closed form, so that the zeros come out with the signs the reference's product gives them.
+    float R[16] = {0}, T[16] = {0};
+    for (int c = 0; c < 3; c++) { R[4 * c + 0] = m_right[c]; R[4 * c + 1] = m_up[c]; R[4 * c + 2] = m_forward[c]; }
+    R[15] = 1.0f;
+    T[0] = T[5] = T[10] = T[15] = 1.0f;
+    T[12] = -m_position[0]; T[13] = -m_position[1]; T[14] = -m_position[2];
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++) {
+            volatile float a = R[0 + i] * T[4 * j + 0], b = R[4 + i] * T[4 * j + 1], c = R[8 + i] * T[4 * j + 2], d = R[12 + i] * T[4 * j + 3];
+            volatile float s = a + b;
+            s = s + c;
+            s = s + d;
+            view[4 * j + i] = s;
+        }
 }
 
 float Camera::getHTanFov() const { return std::tan(0.5f * 0.01745f * m_fov); }

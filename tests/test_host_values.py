@@ -109,3 +109,24 @@ def test_host_sky_equals_the_reference_skymanager(mm):
             assert ref.ref_host_sky(e, a, turbidity, wind.ctypes.data, t, phase, rsun.ctypes.data, rsky.ctypes.data) == 0
             assert np.array_equal(sun.view(np.uint32), rsun.view(np.uint32)), (e, a, sun, rsun)
             assert np.array_equal(sky.view(np.uint32), rsky.view(np.uint32)), (e, a, sky, rsky)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HOST), reason="oracle/_ref/libref_host.so not built (reference tree absent)")
+def test_host_camera_equals_the_reference_camera(mm):
+    """mm_host_camera against the reference's OWN Camera class (camera.h / camera.cpp compiled from /root/reference), driven to a
+    yaw / pitch the way the app's mouse handler does (camera.cpp:147-155) and read out exactly as VulkanApplication.cpp:362-368 fills
+    UniformCameraObject: view (incl. the signs of its zeros), glm::perspective with the y flip, position, aspect, tan(fov/2) --
+    all 160 bytes."""
+    import ctypes as C
+    ref = C.CDLL(REF_HOST)
+    ref.ref_host_camera.argtypes = [C.c_void_p] + [C.c_float] * 5 + [C.c_void_p]
+    rng = np.random.default_rng(0)
+    cases = [((0, 1, 1), -np.pi / 2, -20 * 0.01745, 45.0), ((0, 1, 1), -np.pi / 2, -10 * 0.01745, 45.0), ((3, 1, 2), -np.pi / 2 + 0.01, -0.3, 45.0),
+             ((0, 0, 0), 0.0, 0.0, 45.0), ((1, 2, 3), 1.0, 1.5607, 60.0)]
+    cases += [(tuple(float(x) for x in rng.uniform(-500, 500, 3)), float(rng.uniform(-np.pi, np.pi)), float(rng.uniform(-1.5, 1.5)),
+               float(rng.uniform(20, 90))) for _ in range(3000)]
+    for pos, yaw, pitch, fov in cases:
+        cam = mm.host_camera(pos, yaw, pitch, fov, np.float32(1920.0) / np.float32(1080.0))
+        want, p = np.zeros(40, np.float32), np.asarray(pos, np.float32)
+        assert ref.ref_host_camera(p.ctypes.data, yaw, pitch, fov, 1920.0, 1080.0, want.ctypes.data) == 0
+        assert np.array_equal(cam.view(np.uint32), want.view(np.uint32)), (pos, yaw, pitch, fov)
