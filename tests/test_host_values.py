@@ -130,3 +130,21 @@ def test_host_camera_equals_the_reference_camera(mm):
         want, p = np.zeros(40, np.float32), np.asarray(pos, np.float32)
         assert ref.ref_host_camera(p.ctypes.data, yaw, pitch, fov, 1920.0, 1080.0, want.ctypes.data) == 0
         assert np.array_equal(cam.view(np.uint32), want.view(np.uint32)), (pos, yaw, pitch, fov)
+
+
+def test_block_row_plans_are_permutations_for_every_mode_and_block_height(mm):
+    import scenes
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        cam = mm.host_camera(tuple(rng.uniform(-100, 100, 3)), float(rng.uniform(-3, 3)), float(rng.uniform(-1.4, 1.4)), 45.0, 1920.0 / 1080.0)
+        H = int(rng.integers(1, 2200))
+        stride = int(rng.integers(1, 9))
+        begin = int(rng.integers(0, stride))
+        block = int(rng.choice([1, 2, 4, 8, 16]))
+        bh = int(rng.choice([2, 4, 8]))
+        for mode in (mm.MM_FULL, mm.MM_FULL | mm.MM_ROWS_SNAKE, mm.MM_PHASE16):
+            order = mm.plan_block_rows(cam, H, mode, begin, stride, block, bh)
+            owned = (H + 3) // 4 if mode == mm.MM_PHASE16 else len(mm.multigpu.owned_rows(H, begin, stride, block, bool(mode & mm.MM_ROWS_SNAKE)))
+            if mode != mm.MM_PHASE16:
+                owned = -(-owned // block) * block          # the kernel enumerates whole row blocks of the partition
+            assert sorted(order.tolist()) == list(range(-(-owned // bh))), (H, stride, begin, block, bh, mode)
