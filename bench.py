@@ -109,6 +109,62 @@ def workload_Q(oracle_binding, sc, rows_step, kernel_filter):
             "lit": float(rows[..., 3].mean()), "pixels": npx, "seconds": dt}
 
 
+def _ref_shader_worker(job):
+    """One process of the reference-shader timing: the reference's own compute-clouds.comp (oracle/_ref/libref_cc.so) over a
+    slice of rows of a 1920x1080 frame, every pixel of those rows (4 phase calls per row group)."""
+    import ctypes as C
+    import _pkg
+    import oracle_binding as ob
+    import scenes
+    cfg, rows, filt = job
+    mm = _pkg.load_package()
+    assets = scenes.load_assets()
+    sc = scenes.make_scene(mm, cfg, assets)
+    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=filt, pow_mode=ob.OM_POW_LIBM)
+    ref = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_cc.so"))
+    ref.ref_cc_run.argtypes = [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+
+    class Ctx(C.Structure):
+        _fields_ = [("scene", C.c_void_p), ("filter", C.c_int)]
+    ctx = Ctx(S.s, filt)
+    out = np.zeros((1080, 1920, 4), np.float32)
+    cam, sky = np.ascontiguousarray(sc["cam"], np.float32), np.ascontiguousarray(sc["sky"], np.float32)
+    cb = C.cast(ob.lib().om_sample_callback, C.c_void_p)
+    t0 = time.perf_counter()
+    npx = 0
+    for y in rows:
+        for ox in range(4):
+            sun = np.ascontiguousarray(sc["sun"], np.float32).copy()
+            sun[11] = float((y % 4) * 4 + ox)                         # sun.color.a selects the 1-of-16 pixel phase (CC:292)
+            ids = np.stack([np.arange(480, dtype=np.uint32), np.full(480, y // 4, np.uint32)], 1).copy()
+            ref.ref_cc_run(ob._p(cam), ob._p(sun), ob._p(sky), cb, C.byref(ctx), ob._p(ids), len(ids), ob._p(out), None, None)
+            npx += 480
+    return npx, time.perf_counter() - t0, float(out[rows[0], :8].sum())
+
+
+def time_reference_shader_build(cfg, filt, rows_step, cores):
+    """Throughput of the reference's own shader text compiled for the CPU (single-threaded by construction: its uniform blocks are
+    globals), one process per core; None when it is not available (no _ref build, or a frame the shader's hard-coded 1920x1080
+    does not cover)."""
+    import multiprocessing as mp
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_cc.so")):
+        return None
+    try:
+        rows = list(range(0, 1080, rows_step))
+        chunks = [rows[i::cores] for i in range(cores) if rows[i::cores]]
+        with mp.get_context("spawn").Pool(len(chunks)) as pool:
+            t0 = time.perf_counter()
+            res = pool.map(_ref_shader_worker, [(cfg, c, filt) for c in chunks])
+            wall = time.perf_counter() - t0
+        busy = max(r[1] for r in res)                      # slowest worker's compute time (excludes process start-up and asset loading)
+        npx = sum(r[0] for r in res)
+        return {"value": npx / busy / 1e6, "unit": "Mpix/s", "processes": len(chunks), "pixels": npx, "seconds_slowest_worker": busy,
+                "seconds_wall_incl_startup": wall,
+                "what": "the reference's own compute-clouds.comp, rewritten lexically to C++ and compiled for the CPU (oracle/_ref/libref_cc.so), one process per core"}
+    except Exception as e:                                 # never let the extra measurement break the arm
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args):
     """CPU arm: the reference's GLSL cannot be built here (no glslang / Vulkan / lavapipe), so this times the
     oracle PORT of compute-clouds.comp on all host cores, on a bounded row sample of the same frame."""
@@ -134,6 +190,9 @@ def run_reference(args):
     dt = sum(times) / len(times)
     v = npx / dt / 1e6
     sample = f"every {rows_step}th row of the {sc['W']}x{sc['H']} {args.config} frame ({npx} px per step), OpenMP over rows"
+    ref_build = None
+    if sc["W"] == 1920 and sc["H"] == 1080:
+        ref_build = time_reference_shader_build(args.config, oracle_filter(ob, args.filter), max(rows_step * 4, 1), cores)
     print(json.dumps({
         "impl": "reference", "metric": "cloud-march throughput", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "ms_per_full_frame_extrapolated": sc["W"] * sc["H"] / v / 1e3,
@@ -143,6 +202,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": sample,
                          "note": "oracle port of compute-clouds.comp (bit-identical to the reference's own shader text executed on the CPU, tests/test_reference_shader.py); stands in for the reference shader on lavapipe, which cannot run here"},
         "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_shader_build": ref_build,
         "gpu_launches": 0,
     }))
 
