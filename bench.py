@@ -421,6 +421,18 @@ def main():
                            "L2 flushed between frames; ms_per_frame = sum of the two kernels' CUDA-event times, stream_ms = one event pair around both "
                            "launches issued from this Python binding"}
 
+    # ---- texture-pipe ceiling measured live: L1-resident filtered fetches, bilinear (curl noise, 64 KB) and trilinear
+    # (hi-res volume, 128 KB); reported beside the nominal 148 SM x 4 quads/clk x f_SM
+    tex_peak = None
+    if world == 1:
+        try:
+            ms2, q2 = cs.measureTexPeak(mm.MM_TEX_CURL, 4096)
+            ms3, q3 = cs.measureTexPeak(mm.MM_TEX_HIRES, 4096)
+            tex_peak = {"bilinear_2d_Gquad_s": q2 / 1e9, "trilinear_3d_Gquad_s": q3 / 1e9, "ms": [ms2, ms3],
+                        "how": "mm_measure_tex_peak: 148 x 8 blocks x 256 threads x 4096 filtered fetches from an L1-resident texture, CUDA events"}
+        except Exception as e:                      # the ceiling is supplementary: never let it break the bench line
+            tex_peak = {"unavailable": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         peaks, which = measured_peaks()
         import oracle_binding as ob
@@ -443,6 +455,11 @@ def main():
                                "traffic": None, "Q_quads_per_pixel": wq["Q"], "loop_trips_per_pixel": wq["trips"], "lit_steps_per_pixel": wq["lit"],
                                "peak_source": f"148 SM x 4 bilinear quads/clk x sm_max_mhz ({which} clock); algorithmic quads from the oracle's fetch counters",
                                "hbm_floor_ms": W * H * 16 / (peaks["hbm_gbs"] * 1e9) * 1e3}
+            if tex_peak:
+                out["roofline"]["measured_tex_peak"] = tex_peak
+                best = max(tex_peak.get("bilinear_2d_Gquad_s", 0.0), tex_peak.get("trilinear_3d_Gquad_s", 0.0))
+                if best > 0:
+                    out["roofline"]["frac_of_measured_peak"] = achieved / 1e9 / best
             # second roofline: the march is FP32 / instruction-issue bound.  Warp-instructions per frame of this
             # exact command come from the committed ncu capture (profiles/); peak = 148 SM x 4 schedulers x f_SM.
             prof = os.path.join(ROOT, "profiles", f"r01b_{args.filter}.summary.csv")        # capture of the current kernel revision

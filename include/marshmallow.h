@@ -187,6 +187,11 @@ MM_API int mm_sample(mm_ctx *ctx, int slot, int filter_mode, const float *uvw_ho
 /* the deterministic pow of the decision path, evaluated on the GPU (bit-exactness probe) */
 MM_API int mm_det_pow(mm_ctx *ctx, const float *x_host, const float *y_host, int n, float *out_host);
 
+/* texture-pipe ceiling: filtered fetches per second from the texture bound to `slot` when it is L1-resident (use MM_TEX_CURL, 64 KB,
+ * for the bilinear figure and MM_TEX_HIRES, 128 KB, for the trilinear one); `iters` fetches per thread of one full wave of blocks.
+ * Reported as bilinear-quad operations per second (a trilinear fetch counts as two), the unit of bench.py's texture roofline. */
+MM_API int mm_measure_tex_peak(mm_ctx *ctx, int slot, int iters, float *ms_out, double *quads_per_second_out);
+
 /* exhaustive self-test of the exact divide-by-constant sequence the march uses (csrc/cloud_march.cu,
  * div_const): for constant number `which` (0 .. count-1; MM_ERR_ARG beyond) compares it with the IEEE
  * divide over every binary32 dividend and returns the number of mismatching bit patterns (must be 0). */

@@ -86,6 +86,7 @@ def load_library():
         "mm_last_kernel_ms": (i32, [vp, fp]),
         "mm_sample": (i32, [vp, i32, i32, vp, i32, vp]),
         "mm_det_pow": (i32, [vp, vp, vp, i32, vp]),
+        "mm_measure_tex_peak": (i32, [vp, i32, i32, fp, C.POINTER(C.c_double)]),
         "mm_selftest_div": (i32, [vp, i32, fp, C.POINTER(C.c_uint64)]),
         "mm_alloc_device": (i32, [vp, sz, C.POINTER(vp)]),
         "mm_free_device": (i32, [vp, vp]),

@@ -798,6 +798,31 @@ int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, f
     return MM_OK;
 }
 
+int mm_measure_tex_peak(mm_ctx *ctx, int slot, int iters, float *ms_out, double *quads_per_second_out) {
+    if (!ctx || !ms_out || !quads_per_second_out) return MM_ERR_ARG;
+    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].obj) return fail(ctx, MM_ERR_STATE, "mm_measure_tex_peak: slot %d not bound", slot);
+    if (iters < 2 || iters > (1 << 20)) return fail(ctx, MM_ERR_ARG, "mm_measure_tex_peak: iters %d out of range", iters);
+    CU(cudaSetDevice(ctx->device));
+    const TexSlot &t = ctx->tex[slot];
+    const int blocks = 148 * 8;                                   // one wave of 256-thread blocks on every SM
+    iters += iters & 1;
+    float4 *sink = nullptr;
+    CU(cudaMalloc(&sink, (size_t)blocks * 256 * sizeof(float4)));
+    cudaError_t e = launch_tex_peak(t.obj, t.is3d ? 1 : 0, t.w, 64, blocks, sink, ctx->stream);        // warm-up: fills L1, loads the module
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev0, ctx->stream);
+    if (e == cudaSuccess) e = launch_tex_peak(t.obj, t.is3d ? 1 : 0, t.w, iters, blocks, sink, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev1, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(ctx->ev1);
+    float ms = 0.0f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cudaFree(sink);
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "mm_measure_tex_peak: %s", cudaGetErrorString(e));
+    *ms_out = ms;
+    double fetches = (double)blocks * 256.0 * (double)iters;
+    *quads_per_second_out = ms > 0.0f ? fetches * (t.is3d ? 2.0 : 1.0) / ((double)ms * 1e-3) : 0.0;
+    return MM_OK;
+}
+
 int mm_selftest_div(mm_ctx *ctx, int which, float *constant_out, unsigned long long *mismatches_out) {
     if (!ctx || !constant_out || !mismatches_out) return MM_ERR_ARG;
     if (which < 0 || which >= selftest_div_count()) return MM_ERR_ARG;

@@ -105,6 +105,7 @@ cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, int lanes_per_ray, cudaStream_t stream);
 void march_block_shape(int lanes_per_ray, int *block_w, int *block_h);   // pixels per block of the variant that will run
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
+cudaError_t launch_tex_peak(cudaTextureObject_t obj, int is3d, int width, int iters, int blocks, float4 *sink, cudaStream_t stream);
 cudaError_t launch_det_pow(const float *x, const float *y, int n, float *out, cudaStream_t stream);
 cudaError_t launch_pack_pairs(const uchar4 *src, float4 *dst, int w, int h, int d, int placement_layout, cudaStream_t stream);
 int selftest_div_count();

@@ -266,6 +266,12 @@ class ComputeShader:
         self._check(self._lib.mm_sample(self._ctx, slot, filter_mode, _ptr(uvw), uvw.shape[0], _ptr(out)))
         return out
 
+    def measureTexPeak(self, slot, iters=4096):
+        """-> (ms, bilinear-quad operations per second) of an L1-resident filtered-fetch microbenchmark on `slot`"""
+        ms, q = C.c_float(), C.c_double()
+        self._check(self._lib.mm_measure_tex_peak(self._ctx, slot, iters, C.byref(ms), C.byref(q)))
+        return ms.value, q.value
+
     def selftestDiv(self, which):
         c, bad = C.c_float(), C.c_uint64()
         rc = self._lib.mm_selftest_div(self._ctx, which, C.byref(c), C.byref(bad))

@@ -480,3 +480,17 @@ def test_randomised_scenes_match_their_oracles(mm, oracle, assets):
             cs.close()
             rep = oracle.parity_report(ref, img, rcnt, cnt)
             assert rep["counter_mismatch_pixels"] == 0 and rep["alpha_identical_frac"] == 1.0 and rep["max_abs_diff_8bit"] <= 1, (i, mode, over, rep)
+
+
+def test_texture_peak_microbenchmark_reports_a_plausible_ceiling(mm, assets):
+    """mm_measure_tex_peak: L1-resident filtered fetches.  A B200's nominal ceiling is 148 SM x 4 quads/clk x 1.965 GHz =
+    1.16 Tquad/s; the measurement must be a positive rate of that order (and fail loudly on an unbound slot)."""
+    cs = mm.ComputeShader(0, (8, 8), curl=assets["curl"], hiRes=assets["hires"])
+    ms2, q2 = cs.measureTexPeak(mm.MM_TEX_CURL, 2048)
+    ms3, q3 = cs.measureTexPeak(mm.MM_TEX_HIRES, 2048)
+    print("tex peak: bilinear %.1f Gquad/s (%.3f ms), trilinear %.1f Gquad/s (%.3f ms)" % (q2 / 1e9, ms2, q3 / 1e9, ms3))
+    assert ms2 > 0 and ms3 > 0
+    assert 2e10 < q2 < 1e13 and 2e10 < q3 < 1e13
+    with pytest.raises(mm.MarshmallowError):
+        cs.measureTexPeak(mm.MM_TEX_LOWRES, 2048)
+    cs.close()
