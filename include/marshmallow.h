@@ -113,6 +113,9 @@ MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
  * chosen per dispatch from its size: small dispatches (MM_PHASE16, row-sharded frames on several GPUs) get more lanes. */
 MM_API int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
+/* one frame over n contexts of one process (one per GPU): context i marches partition i of n (row blocks of row_block rows) on
+ * streams[i] (NULL: each context's own stream).  Returns the first failing context's status. */
+MM_API int mm_dispatch_multi(mm_ctx **ctxs, int n, int mode, int row_block, void **streams);
 MM_API int mm_synchronize(mm_ctx *ctx);
 /* host-only diagnostics (no device needed): the order in which mm_dispatch would execute the block rows (block_h rows of the
  * partition's compact row index each) of such a dispatch, most expensive first; order_out needs ceil(owned_rows / block_h)

@@ -16,5 +16,5 @@ from .capi import (  # noqa: F401
     MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES,
     MarshmallowError, library_path, load_library, exported_symbols, host_sky, host_camera, plan_block_rows,
 )
-from .host import ComputeShader, SkyManager, Camera  # noqa: F401
+from .host import ComputeShader, SkyManager, Camera, dispatchMulti  # noqa: F401
 from . import multigpu  # noqa: F401

@@ -66,6 +66,7 @@ def load_library():
         "mm_set_filter_mode": (i32, [vp, i32]),
         "mm_set_lanes_per_ray": (i32, [vp, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
+        "mm_dispatch_multi": (i32, [C.POINTER(vp), i32, i32, i32, C.POINTER(vp)]),
         "mm_synchronize": (i32, [vp]),
         "mm_plan_block_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, C.POINTER(i32)]),
         "mm_bind_previous_linear": (i32, [vp, vp, sz]),

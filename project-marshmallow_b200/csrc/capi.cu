@@ -337,6 +337,19 @@ int mm_bind_output_external_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, int w, i
     return size_counters(ctx);
 }
 
+// One frame sharded over n contexts of ONE process (one per GPU, or several on one GPU): context i marches partition i of n.  The
+// contexts' output bindings decide where the pixels land (the same image, mapped into every device, assembles the frame in place).
+int mm_dispatch_multi(mm_ctx **ctxs, int n, int mode, int row_block, void **streams) {
+    if (!ctxs || n <= 0) return MM_ERR_ARG;
+    for (int i = 0; i < n; i++)
+        if (!ctxs[i]) return MM_ERR_ARG;
+    for (int i = 0; i < n; i++) {
+        int rc = mm_dispatch(ctxs[i], mode, i, n, row_block, streams ? streams[i] : nullptr);
+        if (rc != MM_OK) return rc;                              // mm_last_error(ctxs[i]) has the reason
+    }
+    return MM_OK;
+}
+
 int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes) {
     if (!ctx) return MM_ERR_ARG;
     if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8)

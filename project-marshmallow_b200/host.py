@@ -57,6 +57,16 @@ class Camera:
         return capi.host_camera(self.position, self.yaw, self.pitch, self.fov, self.aspect)
 
 
+def dispatchMulti(shaders, mode=capi.MM_FULL, row_block=8):
+    """One frame sharded over several ComputeShader contexts of this process (mm_dispatch_multi): context i marches partition i."""
+    lib = capi.load_library()
+    arr = (C.c_void_p * len(shaders))(*[s._ctx.value for s in shaders])
+    rc = lib.mm_dispatch_multi(arr, len(shaders), mode, row_block, None)
+    if rc:
+        bad = next((s for s in shaders if lib.mm_last_error(s._ctx)), shaders[0])
+        raise MarshmallowError(rc, lib.mm_last_error(bad._ctx).decode())
+
+
 class ComputeShader:
     def __init__(self, device, extent, placement=None, nightSky=None, curl=None, lowRes=None, hiRes=None):
         self._lib = capi.load_library()

@@ -494,3 +494,28 @@ def test_texture_peak_microbenchmark_reports_a_plausible_ceiling(mm, assets):
     with pytest.raises(mm.MarshmallowError):
         cs.measureTexPeak(mm.MM_TEX_LOWRES, 2048)
     cs.close()
+
+
+def test_dispatch_multi_assembles_one_frame_from_several_contexts(mm, assets):
+    """mm_dispatch_multi: n contexts of one process (here three on the same GPU, bound to the same image) each march their
+    partition; the frame equals a single context's full dispatch bit for bit."""
+    import torch
+    W, H = 210, 119
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    full, _ = _render(mm, sc, mm.MM_FILTER_HW, counters=False)
+    t = torch.full((H, W, 4), -7.0, dtype=torch.float32, device="cuda")
+    shaders = []
+    for _ in range(3):
+        cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                              lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+        cs.bindOutput(t.data_ptr())
+        cs.setFilterMode(mm.MM_FILTER_HW)
+        cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+        shaders.append(cs)
+    mm.dispatchMulti(shaders, mm.MM_FULL, 8)
+    for cs in shaders:
+        cs.synchronize()
+    img = t.cpu().numpy()
+    for cs in shaders:
+        cs.close()
+    assert np.array_equal(img.view(np.uint32), full.view(np.uint32))
