@@ -202,6 +202,9 @@ def parity_report(ref_img, test_img, ref_cnt=None, test_cnt=None):
         "float_identical_frac": float((ref_img == test_img).all(axis=-1).mean()),
         "alpha_identical_frac": float((ref_img[..., 3] == test_img[..., 3]).mean()),
     }
+    # raw HDR floats: relative error percentiles over all channels
+    rel = (np.abs(ref_img.astype(np.float64) - test_img.astype(np.float64)) / np.maximum(np.abs(ref_img.astype(np.float64)), 1e-6)).ravel()
+    rep["rel_err_p50"], rep["rel_err_p99"], rep["rel_err_max"] = (float(x) for x in (np.percentile(rel, 50), np.percentile(rel, 99), rel.max()))
     if ref_cnt is not None and test_cnt is not None:
         rep["branch_flip_pixels"] = int((ref_cnt[..., 0] != test_cnt[..., 0]).sum())
         rep["counter_mismatch_pixels"] = int((ref_cnt != test_cnt).any(axis=-1).sum())
