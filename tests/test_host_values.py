@@ -148,3 +148,17 @@ def test_block_row_plans_are_permutations_for_every_mode_and_block_height(mm):
             if mode != mm.MM_PHASE16:
                 owned = -(-owned // block) * block          # the kernel enumerates whole row blocks of the partition
             assert sorted(order.tolist()) == list(range(-(-owned // bh))), (H, stride, begin, block, bh, mode)
+
+
+def test_config_files_match_the_scene_definitions(mm, assets):
+    """configs/*.json (tools/make_configs.py) carry the same frozen inputs as tests/scenes.py, down to the uniform blocks' floats."""
+    import json
+    import scenes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in scenes.CONFIGS:
+        doc = json.load(open(os.path.join(root, "configs", name + ".json")))
+        sc = scenes.make_scene(mm, name, assets)
+        assert (doc["width"], doc["height"]) == (sc["W"], sc["H"])
+        blocks = doc["uniform_blocks_f32"]
+        for key, arr in (("UniformCameraObject_160B", sc["cam"]), ("UniformSunObject_116B", sc["sun"]), ("UniformSkyObject_52B", sc["sky"])):
+            assert np.array_equal(np.asarray(blocks[key], np.float32), arr), (name, key)
