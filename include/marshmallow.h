@@ -105,13 +105,23 @@ MM_API int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *
 /* ---- dispatch: replaces bindShader + vkCmdDispatch + vkQueueSubmit (Shader.h:358-376,
  * VulkanApplication.cpp:1062-1071, 168-177).  Asynchronous on `stream` (a cudaStream_t, or NULL for
  * the context's own stream).  Rows are partitioned in blocks of row_block rows; this call marches
- * block b when (b - row_begin) % row_stride == 0 and b >= row_begin (single GPU: 0,1,1). */
+ * block b when b % row_stride == row_begin; 0 <= row_begin < row_stride is required (single GPU: 0,1,1).
+ * MM_PHASE16 requires sun.color.a in [0,16) (the engine keeps it there, VulkanApplication.cpp:384). */
 MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
 /* scheduling knob, never changes results: lanes that share one ray.  1 = one thread per ray; 2, 4, 8 = that many
  * consecutive loop trips of a ray are evaluated side by side and replayed through the loop's state machine in order
  * (shortens the dependent chain of a ray 1.9x / 3.7x / 6.7x for 2 / 8 / 17 % more density evaluations); 0 (default) =
  * chosen per dispatch from its size: small dispatches (MM_PHASE16, row-sharded frames on several GPUs) get more lanes. */
 MM_API int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes);
+/* scheduling knob, never changes results: how the pixels of a dispatch reach the warps (one lane per ray only; the ray-split
+ * kernels keep a static grid).  Replaces the fixed workgroup grid of VulkanApplication.cpp:1062-1071.
+ *   MM_SCHED_STATIC      one thread block per 16x8 pixel tile, block rows launched in cost order
+ *   MM_SCHED_PERSISTENT  one resident wave of warps pulling 8x4 pixel tiles, most expensive first, from an atomic queue in device
+ *                        memory; refill_lanes = 32 (or 0): a warp takes a new tile when all its rays are done; 16 / 8: as soon as
+ *                        that many lanes hold finished rays, those lanes store their pixels and are refilled from the queue
+ *   MM_SCHED_AUTO        (default) MM_SCHED_PERSISTENT */
+enum mm_scheduler { MM_SCHED_AUTO = 0, MM_SCHED_STATIC = 1, MM_SCHED_PERSISTENT = 2 };
+MM_API int mm_set_scheduler(mm_ctx *ctx, int scheduler, int refill_lanes);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
 /* one frame over n contexts of one process (one per GPU): context i marches partition i of n (row blocks of row_block rows) on
  * streams[i] (NULL: each context's own stream).  Returns the first failing context's status. */

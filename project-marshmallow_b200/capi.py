@@ -15,6 +15,7 @@ HEADER = os.path.join(HERE, "..", "include", "marshmallow.h")
 MM_FULL, MM_PHASE16 = 0, 1
 MM_ROWS_SNAKE = 0x100
 MM_FILTER_EXACT, MM_FILTER_HW, MM_FILTER_HYBRID = 0, 1, 2
+MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT = 0, 1, 2
 MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES = range(5)
 
 
@@ -65,6 +66,7 @@ def load_library():
         "mm_alloc_output": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]),
         "mm_set_filter_mode": (i32, [vp, i32]),
         "mm_set_lanes_per_ray": (i32, [vp, i32]),
+        "mm_set_scheduler": (i32, [vp, i32, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
         "mm_dispatch_multi": (i32, [C.POINTER(vp), i32, i32, i32, C.POINTER(vp)]),
         "mm_synchronize": (i32, [vp]),

@@ -27,7 +27,7 @@ using namespace mm;
 struct TexSlot {
     cudaArray_t array = nullptr;
     cudaTextureObject_t obj = 0;
-    float4 *pairs = nullptr;      // EXACT-mode pair-major copy (not kept for the night-sky map)
+    float4 *pairs = nullptr;      // FP32-sampler pair-major copy, built on first use by ensure_pairs (never in MM_FILTER_HW)
     int w = 0, h = 0, d = 0;
     bool is3d = false;
 };
@@ -60,6 +60,10 @@ struct mm_ctx {
     float *post_plane = nullptr;   // god-ray alpha plane of mm_post_chain
     size_t post_plane_bytes = 0;
     int lanes_per_ray = 0;         // mm_set_lanes_per_ray: 0 = chosen per dispatch, 1, 2, 4, 8
+    int scheduler = MM_SCHED_AUTO; // mm_set_scheduler: static grid (K1) or persistent warps with a dynamic queue (K1p)
+    int refill = 32;               // K1p: dead lanes that trigger a refill (32 = a whole tile at a time)
+    unsigned *queue = nullptr;     // K1p work-queue counter (device)
+    int sm_count = 148;
     char err[512];
 };
 
@@ -109,11 +113,13 @@ int mm_create(int device, mm_ctx **out) {
     ctx = new (std::nothrow) mm_ctx();
     if (!ctx) return fail(nullptr, MM_ERR_ARG, "out of host memory");
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
     ctx->err[0] = 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->queue, 2 * sizeof(unsigned));
     if (e != cudaSuccess) {
         fail(nullptr, MM_ERR_CUDA, "mm_create: %s", cudaGetErrorString(e));
         delete ctx;
@@ -148,6 +154,7 @@ int mm_destroy(mm_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->post_plane) cudaFree(ctx->post_plane);
+    if (ctx->queue) cudaFree(ctx->queue);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -161,7 +168,6 @@ static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, i
     TexSlot &s = ctx->tex[slot];
     free_slot(s);
     s.w = w; s.h = h; s.d = d; s.is3d = is3d;
-    size_t n = (size_t)w * h * d;
     cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
     if (is3d) {
         CU(cudaMalloc3DArray(&s.array, &fmt, make_cudaExtent(w, h, d)));
@@ -184,8 +190,32 @@ static int bind_texels(mm_ctx *ctx, int slot, const uchar4 *src, int w, int h, i
     td.readMode = cudaReadModeNormalizedFloat;                                         // RGBA8_UNORM (Texture.h:29,85)
     td.normalizedCoords = 1;
     CU(cudaCreateTextureObject(&s.obj, &rd, &td, nullptr));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MM_OK;
+}
+
+static int ensure_stage(mm_ctx *ctx, size_t bytes);
+
+// The pair-major binary32 copy of a slot (FP32-sampler modes only; the default texture-unit mode never reads it): built on
+// first use from the texels resident in the slot's cudaArray, ~16x the bytes of the texture (64 MB for the 128^3 volume).
+static int ensure_pairs(mm_ctx *ctx, int slot) {
+    TexSlot &s = ctx->tex[slot];
+    if (s.pairs || !s.array) return MM_OK;
+    size_t n = (size_t)s.w * s.h * s.d;
+    int rc = ensure_stage(ctx, n * 4);
+    if (rc) return rc;
+    if (s.is3d) {
+        cudaMemcpy3DParms cp = {};
+        cp.srcArray = s.array;
+        cp.dstPtr = make_cudaPitchedPtr(ctx->stage, (size_t)s.w * 4, s.w, s.h);
+        cp.extent = make_cudaExtent(s.w, s.h, s.d);
+        cp.kind = cudaMemcpyDeviceToDevice;
+        CU(cudaMemcpy3DAsync(&cp, ctx->stream));
+    } else {
+        CU(cudaMemcpy2DFromArrayAsync(ctx->stage, (size_t)s.w * 4, s.array, 0, 0, (size_t)s.w * 4, s.h, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CU(cudaMalloc(&s.pairs, n * 2 * sizeof(float4)));
-    CU(launch_pack_pairs(src, s.pairs, w, h, d, slot == MM_TEX_PLACEMENT, ctx->stream));
+    CU(launch_pack_pairs(ctx->stage, s.pairs, s.w, s.h, s.d, slot == MM_TEX_PLACEMENT, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return MM_OK;
 }
@@ -358,6 +388,18 @@ int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes) {
     return MM_OK;
 }
 
+int mm_set_scheduler(mm_ctx *ctx, int scheduler, int refill_lanes) {
+    if (!ctx) return MM_ERR_ARG;
+    if (scheduler != MM_SCHED_AUTO && scheduler != MM_SCHED_STATIC && scheduler != MM_SCHED_PERSISTENT)
+        return fail(ctx, MM_ERR_ARG, "mm_set_scheduler: unknown scheduler %d", scheduler);
+    if (refill_lanes == 0) refill_lanes = 32;
+    if (refill_lanes != 32 && refill_lanes != 16 && refill_lanes != 8)
+        return fail(ctx, MM_ERR_ARG, "mm_set_scheduler: refill_lanes %d (0 or 32 = a tile at a time, 16, 8)", refill_lanes);
+    ctx->scheduler = scheduler;
+    ctx->refill = refill_lanes;
+    return MM_OK;
+}
+
 int mm_set_filter_mode(mm_ctx *ctx, int filter) {
     if (!ctx) return MM_ERR_ARG;
     if (filter < MM_FILTER_EXACT || filter > MM_FILTER_HYBRID) return fail(ctx, MM_ERR_ARG, "mm_set_filter_mode: unknown mode %d", filter);
@@ -416,7 +458,7 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
 // Host-only: the execution order mm_dispatch would give the block rows of a dispatch (most expensive first).  No device needed.
 int mm_plan_block_rows(const void *camera160, int h, int mode, int row_begin, int row_stride, int row_block, int block_h,
                        uint16_t *order_out, int *count_out) {
-    if (!camera160 || !order_out || !count_out || h <= 0 || row_stride <= 0 || row_block <= 0 || block_h <= 0 || row_begin < 0) return MM_ERR_ARG;
+    if (!camera160 || !order_out || !count_out || h <= 0 || row_stride <= 0 || row_block <= 0 || block_h <= 0 || row_begin < 0 || row_begin >= row_stride) return MM_ERR_ARG;
     const int snake = (mode & MM_ROWS_SNAKE) ? 1 : 0;
     mode &= ~MM_ROWS_SNAKE;
     if (mode != MM_FULL && mode != MM_PHASE16) return MM_ERR_ARG;
@@ -443,14 +485,24 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     const int snake = (mode & MM_ROWS_SNAKE) ? 1 : 0;
     mode &= ~MM_ROWS_SNAKE;
     if (mode != MM_FULL && mode != MM_PHASE16) return fail(ctx, MM_ERR_ARG, "mm_dispatch: unknown mode %d", mode);
-    if (row_begin < 0 || row_stride <= 0 || row_block <= 0 || (snake && row_begin >= row_stride)) return fail(ctx, MM_ERR_ARG, "mm_dispatch: bad row partition (%d,%d,%d)", row_begin, row_stride, row_block);
+    if (row_begin < 0 || row_stride <= 0 || row_block <= 0 || row_begin >= row_stride)
+        return fail(ctx, MM_ERR_ARG, "mm_dispatch: bad row partition (%d,%d,%d): need 0 <= row_begin < row_stride, row_block > 0", row_begin, row_stride, row_block);
     if (!ctx->have_uniforms) return fail(ctx, MM_ERR_STATE, "mm_dispatch: uniforms were never set");
     if (!ctx->out && !ctx->surf) return fail(ctx, MM_ERR_STATE, "mm_dispatch: no output image bound");
+    // the 1-of-16 pixel phase rides in sun.color.a (CC:292-298, VulkanApplication.cpp:384 keeps it in 0..15); the shader's uint
+    // pixel coordinates reject anything else by wrapping far outside the image -- here it is an argument error
+    if (mode == MM_PHASE16 && !(ctx->sun[11] >= 0.0f && ctx->sun[11] < 16.0f))
+        return fail(ctx, MM_ERR_ARG, "mm_dispatch: MM_PHASE16 needs sun.color.a in [0,16), got %g", (double)ctx->sun[11]);
     static const int need[4] = {MM_TEX_PLACEMENT, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES};
     for (int i = 0; i < 4; i++)
-        if (!ctx->tex[need[i]].pairs) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
+        if (!ctx->tex[need[i]].obj) return fail(ctx, MM_ERR_STATE, "mm_dispatch: texture slot %d not bound", need[i]);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (ctx->filter != FILTER_HW)                            // the FP32-sampler modes read the pair-major copies (built on first use)
+        for (int i = 0; i < TEX_COUNT; i++) {
+            int rc = ensure_pairs(ctx, i);
+            if (rc) return rc;
+        }
 
     MarchParams p;
     memcpy(p.cam, ctx->cam, sizeof p.cam);
@@ -488,17 +540,34 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         // measured (tools/shard_probe3.py, tools/variant_bench.sh): one lane per ray wins from ~3 waves up (4 for the sparser,
         // less coherent rays of a phase dispatch); two lanes win down to under one wave (1080p phase dispatch: 0.45 -> 0.28 ms,
         // 1/8 of a 1080p frame: 0.43 -> 0.33 ms); four and eight only pay for launches far below one wave
-        double waves = (double)p.grid_w * (double)p.owned_rows / (148.0 * 1024.0);
+        double waves = (double)p.grid_w * (double)p.owned_rows / ((double)ctx->sm_count * 1024.0);
         double full = (mode == MM_PHASE16) ? 4.0 : MM_SPLIT_WAVES;
         lanes = waves >= full ? 1 : waves >= 0.75 ? 2 : waves >= 0.3 ? 4 : 8;
     }
+    // the ray-split kernels (K1s) exist for power-of-two march textures only (wrap by mask); the texture unit wraps any extent
+    bool pow2 = true;
+    for (int i = 0; i < 4; i++) pow2 = pow2 && p.tex[need[i]].pow2;
+    if (ctx->filter != FILTER_HW && !pow2) lanes = 1;
+    // K1p (persistent warps + dynamic queue) replaces the static grid whenever a ray has one lane
+    const bool persistent = lanes == 1 && ctx->scheduler != MM_SCHED_STATIC;
     int block_w, block_h;
-    march_block_shape(lanes, &block_w, &block_h);
+    if (persistent) { block_w = TILE_W; block_h = TILE_H; } else march_block_shape(lanes, &block_w, &block_h);
     int nblockrows = (p.owned_rows + block_h - 1) / block_h;
     if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
     order_block_rows(p, p.block_row_order, nblockrows, block_h);
+    int persistent_blocks = 0;
+    p.queue = nullptr; p.n_slots = 0; p.tiles_x = 0;
+    if (persistent) {
+        p.tiles_x = (unsigned)((p.grid_w + TILE_W - 1) / TILE_W);
+        p.n_slots = p.tiles_x * (unsigned)nblockrows * 32u;
+        p.queue = ctx->queue;
+        unsigned tiles = p.tiles_x * (unsigned)nblockrows;
+        unsigned resident = (unsigned)(ctx->sm_count * persistent_blocks_per_sm(ctx->filter));
+        persistent_blocks = (int)std::min(resident, (tiles + 3u) / 4u);
+        CU(cudaMemsetAsync(ctx->queue, 0, 2 * sizeof(unsigned), stream));
+    }
     CU(cudaEventRecord(ctx->ev0, stream));
-    CU(launch_cloud_march(p, ctx->filter, lanes, stream));
+    CU(launch_cloud_march(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->timed = true;
     return MM_OK;
@@ -735,6 +804,11 @@ int mm_cloud_shadow(mm_ctx *ctx, const float *positions_xyz, int n, int on_devic
     if (n == 0) return MM_OK;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (ctx->filter != MM_FILTER_HW) {
+        int rc = ensure_pairs(ctx, TEX_PLACEMENT);
+        if (rc == MM_OK) rc = ensure_pairs(ctx, TEX_LOWRES);
+        if (rc) return rc;
+    }
     ShadowParams p = {};
     memcpy(p.cam, ctx->cam, sizeof p.cam); memcpy(p.sun, ctx->sun, sizeof p.sun); memcpy(p.sky, ctx->sky, sizeof p.sky);
     {   // L = normalize((camera.view * vec4(sun.directionBasis[1].xyz, 0)).xyz); if (L.y < -0.05) L *= -1  (model.frag:216-217)
@@ -794,9 +868,10 @@ int mm_read_counters(mm_ctx *ctx, uint32_t *host_out) {
 
 int mm_sample(mm_ctx *ctx, int slot, int filter, const float *uvw_host, int n, float *out_host) {
     if (!ctx || !uvw_host || !out_host || n < 0) return MM_ERR_ARG;
-    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].pairs) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
+    if (slot < 0 || slot >= TEX_COUNT || !ctx->tex[slot].obj) return fail(ctx, MM_ERR_STATE, "mm_sample: slot %d not bound", slot);
     if (filter != MM_FILTER_EXACT && filter != MM_FILTER_HW) return fail(ctx, MM_ERR_ARG, "mm_sample: filter must be EXACT or HW");
     CU(cudaSetDevice(ctx->device));
+    if (filter == MM_FILTER_EXACT) { int rc = ensure_pairs(ctx, slot); if (rc) return rc; }
     float *duvw = nullptr; float4 *dout = nullptr;
     CU(cudaMalloc(&duvw, (size_t)n * 12 + 16));
     cudaError_t e = cudaMalloc(&dout, (size_t)n * 16 + 16);

@@ -66,6 +66,10 @@ struct MarchParams {
     // cheap, which is what limits strong scaling when a GPU owns only a few waves of tiles.  Built on the host
     // per dispatch (capi.cu, order_block_rows); affects scheduling only, never results.
     uint16_t block_row_order[4096];
+    // K1p (persistent warps, dynamic queue): one counter in device memory, zeroed on the stream before the launch; slots are
+    // numbered tile-major (slot = tile * 32 + lane-in-tile, tiles_x tiles per tile row, tile rows in block_row_order)
+    unsigned *queue;
+    unsigned n_slots, tiles_x;
 };
 
 struct ReprojectParams {
@@ -102,7 +106,9 @@ struct ShadowParams {
 cudaError_t launch_cloud_shadow(const ShadowParams &p, int filter, cudaStream_t stream);
 
 cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
-cudaError_t launch_cloud_march(const MarchParams &p, int filter, int lanes_per_ray, cudaStream_t stream);
+// persistent_blocks > 0: K1p with that many 128-thread blocks (lanes_per_ray must be 1, p.queue zeroed on `stream`); refill 32/16/8
+cudaError_t launch_cloud_march(const MarchParams &p, int filter, int lanes_per_ray, int persistent_blocks, int refill, cudaStream_t stream);
+int persistent_blocks_per_sm(int filter);
 void march_block_shape(int lanes_per_ray, int *block_w, int *block_h);   // pixels per block of the variant that will run
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
 cudaError_t launch_tex_peak(cudaTextureObject_t obj, int is3d, int width, int iters, int blocks, float4 *sink, cudaStream_t stream);

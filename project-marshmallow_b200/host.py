@@ -177,6 +177,10 @@ class ComputeShader:
         """0 = per dispatch (default), 1, 2, 4, 8: scheduling only, results are identical"""
         self._check(self._lib.mm_set_lanes_per_ray(self._ctx, lanes))
 
+    def setScheduler(self, scheduler=capi.MM_SCHED_AUTO, refill_lanes=0):
+        """static grid (K1) or persistent warps pulling tiles from a dynamic queue (K1p); refill_lanes 32/16/8: scheduling only"""
+        self._check(self._lib.mm_set_scheduler(self._ctx, scheduler, refill_lanes))
+
     def dispatch(self, mode=capi.MM_FULL, row_begin=0, row_stride=1, row_block=1, stream=None):
         """stream: None -> the context's own stream; an integer cudaStream_t otherwise (0, the legacy default
         stream that torch calls its default stream, is passed as cudaStreamLegacy = 1)."""

@@ -72,3 +72,15 @@ def make_scene(mm, name, assets, W=None, H=None, time=None, pixel_phase=0, **ove
     tex = {k: assets[k] for k in ("curl", "lowres", "hires")}
     tex["placement"] = assets["placement"] if cfg["placement"] == "shipped" else constant_placement(*cfg["placement"])
     return dict(name=name, W=cfg["W"], H=cfg["H"], cam=cam, sun=sun, sky=sky, textures=tex)
+
+
+def scene_from_config(name, assets):
+    """The same scene dict as make_scene, built from configs/<name>.json alone (frozen uniform blocks; no product library involved):
+    what the CPU reference arm of bench.py binds."""
+    doc = json.load(open(os.path.join(ROOT, "configs", name + ".json")))
+    blocks = doc["uniform_blocks_f32"]
+    tex = {k: assets[k] for k in ("curl", "lowres", "hires")}
+    pl = doc["placement"]
+    tex["placement"] = assets["placement"] if isinstance(pl, str) else constant_placement(pl["constant_R_coverage"], pl["constant_B_type"])
+    return dict(name=name, W=doc["width"], H=doc["height"], cam=np.asarray(blocks["UniformCameraObject_160B"], np.float32),
+                sun=np.asarray(blocks["UniformSunObject_116B"], np.float32), sky=np.asarray(blocks["UniformSkyObject_52B"], np.float32), textures=tex)

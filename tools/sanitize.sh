@@ -12,15 +12,24 @@ W, H = 96, 54
 sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
 cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"], lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
 cs.allocOutput()
+# every march kernel variant: K1 (static grid), K1p (persistent warps; a tile at a time, refill at 16 / 8 dead lanes) and
+# K1s (2, 4, 8 lanes per ray), with and without counters, in the three sampler modes
+variants = [(1, mm.MM_SCHED_STATIC, 0), (1, mm.MM_SCHED_PERSISTENT, 32), (1, mm.MM_SCHED_PERSISTENT, 16), (1, mm.MM_SCHED_PERSISTENT, 8),
+            (2, mm.MM_SCHED_AUTO, 0), (4, mm.MM_SCHED_AUTO, 0), (8, mm.MM_SCHED_AUTO, 0)]
 for counters in (False, True):
     cs.enableCounters(counters)
     for mode in (mm.MM_FILTER_EXACT, mm.MM_FILTER_HW, mm.MM_FILTER_HYBRID):
         cs.setFilterMode(mode)
-        cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
-        cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sc["sun"])
-        cs.dispatch(mm.MM_PHASE16)
-        cs.dispatch(mm.MM_FULL, 1, 3, 2)
-        cs.synchronize()
+        for lanes, sched, refill in variants:
+            cs.setLanesPerRay(lanes)
+            cs.setScheduler(sched, refill)
+            cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+            cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sc["sun"])
+            cs.dispatch(mm.MM_PHASE16)
+            cs.dispatch(mm.MM_FULL, 1, 3, 2)
+            cs.synchronize()
+cs.setLanesPerRay(0)
+cs.setScheduler(mm.MM_SCHED_AUTO, 0)
 cs.tonemapRGBA8()
 import torch
 src = torch.rand((H, W, 4), device="cuda")
