@@ -548,8 +548,9 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     bool pow2 = true;
     for (int i = 0; i < 4; i++) pow2 = pow2 && p.tex[need[i]].pow2;
     if (ctx->filter != FILTER_HW && !pow2) lanes = 1;
-    // K1p (persistent warps + dynamic queue) replaces the static grid whenever a ray has one lane
-    const bool persistent = lanes == 1 && ctx->scheduler != MM_SCHED_STATIC;
+    // K1p (persistent warps + dynamic queue) instead of the static grid: opt-in.  Measured on B200 (profiles/r02_scheduler_ab.txt):
+    // equal to the static grid on whole frames (5.85 vs 5.82 ms at 4K), 2-11 % slower on the row shares of an 8-GPU frame
+    const bool persistent = lanes == 1 && ctx->scheduler == MM_SCHED_PERSISTENT;
     int block_w, block_h;
     if (persistent) { block_w = TILE_W; block_h = TILE_H; } else march_block_shape(lanes, &block_w, &block_h);
     int nblockrows = (p.owned_rows + block_h - 1) / block_h;
@@ -557,11 +558,11 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     order_block_rows(p, p.block_row_order, nblockrows, block_h);
     int persistent_blocks = 0;
     p.queue = nullptr; p.n_slots = 0; p.tiles_x = 0;
-    if (persistent) {
+    if (persistent) {                                             // queue entries are pixel slots, 32 per 8x4 tile
         p.tiles_x = (unsigned)((p.grid_w + TILE_W - 1) / TILE_W);
-        p.n_slots = p.tiles_x * (unsigned)nblockrows * 32u;
-        p.queue = ctx->queue;
         unsigned tiles = p.tiles_x * (unsigned)nblockrows;
+        p.n_slots = tiles * 32u;
+        p.queue = ctx->queue;
         unsigned resident = (unsigned)(ctx->sm_count * persistent_blocks_per_sm(ctx->filter));
         persistent_blocks = (int)std::min(resident, (tiles + 3u) / 4u);
         CU(cudaMemsetAsync(ctx->queue, 0, 2 * sizeof(unsigned), stream));
