@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--filter", default="hw", choices=["exact", "hw", "hybrid"],
                     help="hw (default): texture-unit filtering, parity against the oracle's bit-exact texture-unit model; "
                          "exact / hybrid: FP32 software filtering of the march samples, parity against the oracle's binary32 sampler")
+    ap.add_argument("--arith", default="ieee", choices=["ieee", "fma"],
+                    help="arithmetic definition: ieee (default) = one rounding per operator; fma = the lexical contraction rule (its own oracle)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the N = 1 side blocks (parity_grade, sampler tail, C2, cadence, tex peak, sustained)")
     ap.add_argument("--lanes", type=int, default=0, choices=[0, 1, 2, 4, 8], help="lanes sharing one ray: 0 = chosen per dispatch (default), 1, 2, 4, 8 (scheduling only)")
@@ -112,10 +114,11 @@ def host_threads():
     return os.cpu_count() or 1
 
 
-def workload_Q(oracle_binding, sc, rows_step, kernel_filter):
+def workload_Q(oracle_binding, sc, rows_step, kernel_filter, arith="ieee"):
     """Algorithmic work per pixel: Q = N2D + 2*N3D bilinear-quad ops, from the oracle's counters on
     a row subsample of the same frame (every rows_step-th row)."""
-    S = oracle_binding.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(oracle_binding, kernel_filter))
+    S = oracle_binding.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(oracle_binding, kernel_filter),
+                             arith=oracle_binding.OM_ARITH_FMA if arith == "fma" else oracle_binding.OM_ARITH_IEEE)
     t0 = time.time()
     _, cnt = S.march(sc["W"], sc["H"], row_begin=0, row_stride=rows_step, row_block=1, nthreads=host_threads())
     dt = time.time() - t0
@@ -190,7 +193,8 @@ def run_reference(args):
     sc = scenes.scene_from_config(args.config, scenes.load_assets())
     cores = host_threads()
     rows_step = max(1, int(sc["W"] * sc["H"] / 150e3))     # ~150k pixels per step
-    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(ob, args.filter))
+    S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle_filter(ob, args.filter),
+                 arith=ob.OM_ARITH_FMA if args.arith == "fma" else ob.OM_ARITH_IEEE)
     times = []
     npx = len(range(0, sc["H"], rows_step)) * sc["W"]
     for i in range(args.warmup + args.steps):
@@ -348,6 +352,7 @@ def main():
         s = mm.ComputeShader(local, (scene["W"], scene["H"]), placement=scene["textures"]["placement"], curl=scene["textures"]["curl"],
                              lowRes=scene["textures"]["lowres"], hiRes=scene["textures"]["hires"])
         s.setFilterMode(fmode)
+        s.setArithmetic(mm.MM_ARITH_FMA if args.arith == "fma" else mm.MM_ARITH_IEEE)
         s.setLanesPerRay(args.lanes)
         s.setScheduler(sched, args.refill)
         s.updateUniformBuffers(scene["cam"], None, scene["sky"], scene["sun"])
@@ -495,6 +500,78 @@ def main():
                      "note": f"back-to-back frames in batches of {batch} (one stream synchronize per batch), wall clock, no L2 flush"}
 
     extras = {}
+    if world > 1 and not args.no_extras:
+        # ---- the comparison path SURVEY 8e asks for: every rank marches its rows into a LOCAL image, then the bands are gathered to
+        # rank 0 with grouped NCCL send/recv (torch.distributed.batch_isend_irecv = ncclGroupStart/ncclSend/ncclRecv/ncclGroupEnd) and
+        # scattered into the frame -- against the fused path above, whose kernels store straight into rank 0's image over NVLink.
+        local_img = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+        loc = new_shader(sc)
+        loc.bindOutput(local_img.data_ptr())
+        rows_of = [torch.from_numpy(multigpu.owned_rows(H, r, world, args.row_block)).cuda() for r in range(world)]
+        frame = torch.empty((H, W, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        bufs = [torch.empty((len(rows_of[r]), W, 4), dtype=torch.float32, device="cuda") for r in range(1, world)] if rank == 0 else None
+
+        def gather_once():
+            loc.dispatch(mm.MM_FULL, rank, world, args.row_block, stream=stream.cuda_stream)
+            packed = local_img.index_select(0, rows_of[rank])
+            if rank == 0:
+                reqs = dist.batch_isend_irecv([dist.P2POp(dist.irecv, bufs[r - 1], r) for r in range(1, world)])
+            else:
+                reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, packed, 0)])
+            for q in reqs:
+                q.wait()
+            if rank == 0:
+                frame.index_copy_(0, rows_of[0], packed)
+                for r in range(1, world):
+                    frame.index_copy_(0, rows_of[r], bufs[r - 1])
+        for _ in range(3):
+            gather_once()
+        barrier()
+        gev = []
+        for _ in range(max(3, K // 2)):
+            barrier()
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            gather_once()
+            e1.record(stream)
+            gev.append((e0, e1))
+        barrier()
+        gt = torch.tensor([a.elapsed_time(b) for a, b in gev], dtype=torch.float64, device="cuda")
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        same = None
+        if rank == 0:
+            same = bool(np.array_equal(frame.cpu().numpy().view(np.uint32), dev_frame.view(np.uint32)))
+        loc.close()
+        del local_img, frame, bufs
+        extras["nccl_gather_comparison"] = {"ms_per_frame": float(gt.mean()), "fused_peer_store_ms_per_frame": ms, "gathered_frame_equals_fused_frame": same,
+                                            "what": "local march + index_select of the owned rows + grouped ncclSend/ncclRecv to rank 0 + index_copy into the frame, CUDA events, max over ranks"}
+        # ---- BASELINE configs[1] sharded the same way (strong scaling of the small frame)
+        if args.config != "C2":
+            sc2 = scenes.make_scene(mm, "C2", assets)
+            c2 = new_shader(sc2)
+            sh2 = multigpu.SharedFrame(c2, rank, world, dist)
+            for _ in range(3):
+                c2.dispatch(mm.MM_FULL, rank, world, args.row_block, stream=stream.cuda_stream)
+            barrier()
+            ev2 = []
+            for _ in range(K):
+                barrier()
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                c2.dispatch(mm.MM_FULL, rank, world, args.row_block, stream=stream.cuda_stream)
+                e1.record(stream)
+                ev2.append((e0, e1))
+            barrier()
+            t2 = torch.tensor([a.elapsed_time(b) for a, b in ev2], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            h2 = sha256_of(c2.readOutput()) if rank == 0 else None
+            barrier()
+            sh2.close()
+            c2.close()
+            extras["extra"] = {"C2": {"workload": "C2 1920x1080 noon, full-resolution march, sharded like the headline", "filter": args.filter,
+                                      "ms_per_frame": float(t2.mean()), "value": 1920 * 1080 / float(t2.mean()) / 1e3, "unit": "Mpix/s", "frame_sha256": h2}}
     if world == 1 and not args.no_extras:
         import oracle_binding as ob
         # ---- the gate-meeting sampler modes on the same workload: FP32 filtering of the march samples
@@ -504,6 +581,17 @@ def main():
             t = time_frames(torch, mm, cs, stream, flush, max(3, K // 4))
             grade[name] = {"ms_per_frame": t, "Mpix_s": W * H / t / 1e3,
                            "parity": "bit-exact decisions vs the oracle's texture-unit model" if name == "hw" else "bit-exact decisions vs the oracle's binary32 sampler (the literal north-star gate)"}
+        # ---- the CONTRACTED arithmetic definition beside it: its own oracle, zero branch flips against it
+        # (tests/test_arith_fma_gpu.py); a different definition, reported beside the uncontracted one, never instead of it
+        cs.setArithmetic(mm.MM_ARITH_FMA)
+        fma = {}
+        for name, fm in (("hw", mm.MM_FILTER_HW), ("hybrid", mm.MM_FILTER_HYBRID), ("exact", mm.MM_FILTER_EXACT)):
+            cs.setFilterMode(fm)
+            t = time_frames(torch, mm, cs, stream, flush, max(3, K // 4))
+            fma[name] = {"ms_per_frame": t, "Mpix_s": W * H / t / 1e3}
+        fma["parity"] = "bit-exact decisions vs oracle/cloud_march_oracle_fma.c (pinned to the reference's shader text compiled under the same lexical contraction rule)"
+        grade["arith_fma"] = fma
+        cs.setArithmetic(mm.MM_ARITH_FMA if args.arith == "fma" else mm.MM_ARITH_IEEE)
         cs.setFilterMode(fmode)
         try:
             grade["hw_vs_binary32_oracle"] = sampler_tail(mm, ob, cs, sc)
@@ -594,7 +682,7 @@ def main():
             "ms_per_step": ms, "ms_per_frame": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.config} {W}x{H} full-resolution cloud march (every pixel), shipped CloudPlacement/CurlNoiseFBM/128^3/32^3 textures",
-                       "filter": args.filter, "lanes_per_ray": args.lanes or "per dispatch", "scheduler": args.scheduler + (f", refill {args.refill}" if args.refill else ""),
+                       "filter": args.filter, "arithmetic": args.arith, "lanes_per_ray": args.lanes or "per dispatch", "scheduler": args.scheduler + (f", refill {args.refill}" if args.refill else ""),
                        "l2": "flushed (256 MB write between frames)", "parallelism": f"row-cyclic x{world}, row block {args.row_block}" if world > 1 else "single GPU"},
             "clocks": clocks, "gpu_launches": K, "e2e": e2e, "frame_sha256": frame_hash, "per_rank_kernel_ms": rank_ms,
         }
@@ -602,12 +690,12 @@ def main():
             out["sharded_equals_single_gpu"] = sharded_ok
         if sustained:
             out["sustained"] = sustained
-        for k in ("parity_grade", "scheduler_ms_per_frame", "extra", "reference_cadence"):
+        for k in ("parity_grade", "scheduler_ms_per_frame", "extra", "reference_cadence", "nccl_gather_comparison"):
             if k in extras:
                 out[k] = extras[k]
         if not args.no_cpu_baseline:
             rows_step = max(1, int(W * H / 300e3))
-            wq = workload_Q(ob, sc, rows_step, args.filter)
+            wq = workload_Q(ob, sc, rows_step, args.filter, args.arith)
             texpeak = N_SM * TEXPEAK_QUADS_PER_CLK_PER_SM * peaks["sm_max_mhz"] * 1e6
             achieved = wq["Q"] * W * H / (ms * 1e-3) / world           # per GPU: every rank marches 1/world of the frame's quads in the frame time
             out["roofline"] = {"bound": "tex", "achieved": achieved / 1e9, "peak": texpeak / 1e9, "unit": "Gquad/s", "frac": achieved / texpeak,
@@ -621,7 +709,7 @@ def main():
                     out["roofline"]["frac_of_measured_peak"] = achieved / 1e9 / best
             # second roofline: the march is FP32 / instruction-issue bound.  Warp-instructions and DRAM bytes per launch of
             # this exact command come from the committed ncu capture (profiles/); peak = 148 SM x 4 schedulers x f_SM.
-            prof = os.path.join(ROOT, "profiles", f"r02_{args.config}_{args.filter}.summary.csv")
+            prof = os.path.join(ROOT, "profiles", f"r02_{args.config}_{args.filter}" + ("_fma" if args.arith == "fma" else "") + ".summary.csv")
             if os.path.exists(prof) and world == 1:
                 rows = {l.split(",")[0]: l.strip().split(",") for l in open(prof) if l.count(",") >= 2}
                 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

@@ -62,6 +62,15 @@ enum mm_filter_mode {
     MM_FILTER_HYBRID = 2    /* march decisions: EXACT; the 6 light-cone samples: texture unit */
 };
 
+/* arithmetic definition of the march (see DESIGN.md "arithmetic definitions").  GLSL fixes neither the rounding of `a*b + c` nor
+ * that of pow(); each value below is one complete definition with a bit-exact CPU statement in oracle/ that is pinned to the
+ * reference's own shader text and against which the kernel's decisions are tested (zero branch flips, bit-identical alpha). */
+enum mm_arith_mode {
+    MM_ARITH_IEEE = 0,      /* DEFAULT: every operator rounded once, no contraction (oracle/cloud_march_oracle.c, glsl_env.h) */
+    MM_ARITH_FMA = 1        /* the contraction GLSL permits and GPUs perform, as one lexical rule: a product that is directly an
+                               operand of + or - is fused into it (oracle/cloud_march_oracle_fma.c, glsl_env_fma.h) */
+};
+
 /* ---- context: replaces ComputeShader's constructor/destructor (Shader.h:338-353, Shader.cpp:633-645) */
 MM_API int mm_create(int device, mm_ctx **out);
 MM_API int mm_destroy(mm_ctx *ctx);
@@ -100,6 +109,19 @@ MM_API int mm_set_uniforms(mm_ctx *ctx, const void *camera160, const void *camer
  * mm_alloc_output: convenience, allocates the image inside the context. */
 MM_API int mm_bind_output_linear(mm_ctx *ctx, float *dptr_rgba32f, size_t pitch_bytes, int w, int h);
 MM_API int mm_bind_output_external_fd(mm_ctx *ctx, int opaque_fd, size_t alloc_bytes, int w, int h);
+/* the same import for LINEARLY laid out external memory (VkBuffer, or a VK_IMAGE_TILING_LINEAR image: pitch from
+ * vkGetImageSubresourceLayout): mapped as a device buffer (cudaExternalMemoryGetMappedBuffer) and written with plain stores.
+ * On success the library owns the fd.  Exercised in tests with an fd exported by CUDA's own virtual-memory allocator. */
+MM_API int mm_bind_output_external_buffer_fd(mm_ctx *ctx, int opaque_fd, size_t alloc_bytes, size_t offset_bytes, size_t pitch_bytes,
+                                             int w, int h);
+/* ---- ordering against the engine's queues.  The reference submits the compute work with no fence or semaphore
+ * (VulkanApplication.cpp:168-177) and idles the present queue every frame (:237); a CUDA producer imports the engine's exported
+ * VkSemaphores (opaque fd; timeline != 0 for a timeline semaphore, `value` is then the payload) and waits / signals them on the
+ * dispatch stream:  mm_wait_semaphore(image_free); mm_dispatch(...); mm_signal_semaphore(image_ready).  Slots 0..7 per context. */
+MM_API int mm_import_semaphore_fd(mm_ctx *ctx, int opaque_fd, int timeline, int *slot_out);
+MM_API int mm_wait_semaphore(mm_ctx *ctx, int slot, uint64_t value, void *stream);
+MM_API int mm_signal_semaphore(mm_ctx *ctx, int slot, uint64_t value, void *stream);
+MM_API int mm_release_semaphore(mm_ctx *ctx, int slot);
 MM_API int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *pitch_out);
 
 /* ---- dispatch: replaces bindShader + vkCmdDispatch + vkQueueSubmit (Shader.h:358-376,
@@ -108,6 +130,7 @@ MM_API int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *
  * block b when b % row_stride == row_begin; 0 <= row_begin < row_stride is required (single GPU: 0,1,1).
  * MM_PHASE16 requires sun.color.a in [0,16) (the engine keeps it there, VulkanApplication.cpp:384). */
 MM_API int mm_set_filter_mode(mm_ctx *ctx, int filter_mode);
+MM_API int mm_set_arithmetic(mm_ctx *ctx, int arith_mode);   /* applies to mm_dispatch / mm_render_to_host and to mm_det_pow */
 /* scheduling knob, never changes results: lanes that share one ray.  1 = one thread per ray; 2, 4, 8 = that many
  * consecutive loop trips of a ray are evaluated side by side and replayed through the loop's state machine in order
  * (shortens the dependent chain of a ray 1.9x / 3.7x / 6.7x for 2 / 8 / 17 % more density evaluations); 0 (default) =
@@ -126,6 +149,9 @@ MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int
 /* one frame over n contexts of one process (one per GPU): context i marches partition i of n (row blocks of row_block rows) on
  * streams[i] (NULL: each context's own stream).  Returns the first failing context's status. */
 MM_API int mm_dispatch_multi(mm_ctx **ctxs, int n, int mode, int row_block, void **streams);
+/* contexts on DIFFERENT devices of one process that store into one image: enable peer access from ctx's device to peer's
+ * (no-op for the same device; across processes mm_ipc_open_handle does it) */
+MM_API int mm_enable_peer(mm_ctx *ctx, mm_ctx *peer);
 MM_API int mm_synchronize(mm_ctx *ctx);
 /* host-only diagnostics (no device needed): the order in which mm_dispatch would execute the block rows (block_h rows of the
  * partition's compact row index each) of such a dispatch, most expensive first; order_out needs ceil(owned_rows / block_h)

@@ -54,6 +54,7 @@
 #endif
 
 #include "oracle.h"
+#include "oracle_internal.h"
 
 /* ------------------------------------------------------------------------------------------ */
 /* small vector helpers                                                                         */
@@ -140,11 +141,6 @@ float om_det_powf(float x, float y) {
 
 /* ------------------------------------------------------------------------------------------ */
 /* software sampler: Texture.cpp:29-52 (2D) and :315-338 (3D): LINEAR, REPEAT, LOD 0, RGBA8_UNORM */
-typedef struct {
-    const float *texels;  /* w*h*d*4 floats holding the byte values 0..255 */
-    int w, h, d;
-    const uint8_t *bytes; /* the same texels as bytes (integer sampler model) */
-} ftex;
 
 static inline int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
 static inline float lerpf(float p, float q, float a) { return __builtin_fmaf(a, q - p, p); }
@@ -225,7 +221,7 @@ static void texunit_sample(const ftex *t, int is3d, float u, float v, float w, f
     for (int ch = 0; ch < 4; ch++) out[ch] = texunit_unorm16(acc[ch]);
 }
 
-static void sample2d(const ftex *t, int filter, float u, float v, float out[4]) {
+void om__sample2d(const ftex *t, int filter, float u, float v, float out[4]) {
     if (filter == OM_FILTER_TEXUNIT) { texunit_sample(t, 0, u, v, 0.0f, out); return; }
     int x0, x1, y0, y1; float a, b;
     filter_coord(u, t->w, filter, &x0, &x1, &a);
@@ -241,7 +237,7 @@ static void sample2d(const ftex *t, int filter, float u, float v, float out[4]) 
     }
 }
 
-static void sample3d(const ftex *t, int filter, float u, float v, float w, float out[4]) {
+void om__sample3d(const ftex *t, int filter, float u, float v, float w, float out[4]) {
     if (filter == OM_FILTER_TEXUNIT) { texunit_sample(t, 1, u, v, w, out); return; }
     int x0, x1, y0, y1, z0, z1; float a, b, g;
     filter_coord(u, t->w, filter, &x0, &x1, &a);
@@ -265,19 +261,6 @@ static void sample3d(const ftex *t, int filter, float u, float v, float w, float
 }
 
 /* ------------------------------------------------------------------------------------------ */
-struct om_scene {
-    ftex placement, nightsky, curl, lowres, hires;
-    float *store[5];
-    uint8_t *bstore[5];
-    float cam[40];   /* UniformCameraObject, 160 B: Shader.h:24-29 */
-    float sun[29];   /* UniformSunObject,    116 B: SkyManager.h:8-14 */
-    float sky[13];   /* UniformSkyObject,     52 B: SkyManager.h:28-36 */
-    int filter;      /* OM_FILTER_* */
-    int pow_mode;    /* OM_POW_*    */
-};
-
-typedef struct { uint32_t trips, n2d, n3d, lit; uint32_t *litmask; /* optional: bit k set = loop iteration k was a lit step (k < 256) */ } px_counters;
-
 typedef struct {
     const struct om_scene *s;
     v3 cameraPos, earthCenter, windXYZ;
@@ -327,8 +310,15 @@ int om_scene_set_modes(om_scene *s, int filter, int pow_mode) {
     s->filter = filter; s->pow_mode = pow_mode;
     return 0;
 }
+int om_scene_set_arith(om_scene *s, int arith) {
+    if (!s || (arith != OM_ARITH_IEEE && arith != OM_ARITH_FMA)) return -1;
+    s->arith = arith;
+    return 0;
+}
 
 /* ------------------------------------------------------------------------------------------ */
+#define sample2d om__sample2d
+#define sample3d om__sample3d
 #define ATMOSPHERE_RADIUS 2000000.0f                       /* CC:56 */
 #define ONE_OVER_FOURPI 0.07957747154594767f               /* CC:63 */
 #define THREE_OVER_SIXTEENPI 0.05968310365946075f          /* CC:62 */
@@ -805,7 +795,8 @@ int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_s
             if (mode == OM_PHASE16 && (x % 4) != ox) continue;
             px_counters c = {0, 0, 0, 0, g_litmask ? g_litmask + 8 * ((size_t)y * W + x) : NULL};
             float o[4];
-            march_pixel(s, x, y, W, H, o, &c);
+            if (s->arith == OM_ARITH_FMA) om__march_pixel_fma(s, x, y, W, H, o, &c);
+            else march_pixel(s, x, y, W, H, o, &c);
             size_t i = (size_t)y * W + x;
             memcpy(out_rgba32f + 4 * i, o, 16);
             if (counters) { counters[4 * i] = c.trips; counters[4 * i + 1] = c.n2d; counters[4 * i + 2] = c.n3d; counters[4 * i + 3] = c.lit; }

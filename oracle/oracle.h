@@ -10,6 +10,8 @@ extern "C" {
 enum { OM_TEX_PLACEMENT = 0, OM_TEX_NIGHTSKY = 1, OM_TEX_CURL = 2, OM_TEX_LOWRES = 3, OM_TEX_HIRES = 4 };
 enum { OM_FILTER_FP32 = 0, OM_FILTER_FIX8 = 1, OM_FILTER_TEXUNIT = 2 /* bit-exact model of the B200 texture unit */ };
 enum { OM_POW_DET = 0, OM_POW_LIBM = 1 };
+/* arithmetic definition: one rounding per operator (no contraction), or the lexical fused-multiply-add rule of glsl_env_fma.h */
+enum { OM_ARITH_IEEE = 0, OM_ARITH_FMA = 1 };
 enum { OM_FULL = 0, OM_PHASE16 = 1 };
 
 typedef struct om_scene om_scene;
@@ -19,6 +21,8 @@ void om_scene_destroy(om_scene *s);
 int om_scene_set_texture(om_scene *s, int slot, const uint8_t *rgba8, int w, int h, int d);
 int om_scene_set_uniforms(om_scene *s, const void *camera160, const void *sun116, const void *sky52);
 int om_scene_set_modes(om_scene *s, int filter, int pow_mode);
+int om_scene_set_arith(om_scene *s, int arith);
+float om_det_powf_fma(float x, float y);   /* the contracted definition's deterministic pow (Horner steps fused) */
 int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_stride, int row_block,
              float *out_rgba32f, uint32_t *counters /* 4 per pixel or NULL */, int nthreads);
 void om_set_window(int trips_per_window /* 1 = plain loop; >1 = windowed replay model of the kernel's ray-split mode */);

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libmarshmallow_b200.so")
 DEMO = os.path.join(HERE, "frame_demo")
-CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu", "csrc/reproject.cu", "csrc/post_chain.cu"]
+CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/cloud_march_fma.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu", "csrc/reproject.cu", "csrc/post_chain.cu"]
 CPP_SOURCES = ["host/sky_camera.cpp"]
 HEADERS = ["csrc/common.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h", "host/ComputeShader.h", "host/frame_demo.cpp"]
 

@@ -16,6 +16,7 @@ MM_FULL, MM_PHASE16 = 0, 1
 MM_ROWS_SNAKE = 0x100
 MM_FILTER_EXACT, MM_FILTER_HW, MM_FILTER_HYBRID = 0, 1, 2
 MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT = 0, 1, 2
+MM_ARITH_IEEE, MM_ARITH_FMA = 0, 1
 MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES = range(5)
 
 
@@ -63,10 +64,17 @@ def load_library():
         "mm_set_uniforms": (i32, [vp, vp, vp, vp, vp]),
         "mm_bind_output_linear": (i32, [vp, vp, sz, i32, i32]),
         "mm_bind_output_external_fd": (i32, [vp, i32, sz, i32, i32]),
+        "mm_bind_output_external_buffer_fd": (i32, [vp, i32, sz, sz, sz, i32, i32]),
+        "mm_import_semaphore_fd": (i32, [vp, i32, i32, C.POINTER(i32)]),
+        "mm_wait_semaphore": (i32, [vp, i32, u64, vp]),
+        "mm_signal_semaphore": (i32, [vp, i32, u64, vp]),
+        "mm_release_semaphore": (i32, [vp, i32]),
+        "mm_enable_peer": (i32, [vp, vp]),
         "mm_alloc_output": (i32, [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]),
         "mm_set_filter_mode": (i32, [vp, i32]),
         "mm_set_lanes_per_ray": (i32, [vp, i32]),
         "mm_set_scheduler": (i32, [vp, i32, i32]),
+        "mm_set_arithmetic": (i32, [vp, i32]),
         "mm_dispatch": (i32, [vp, i32, i32, i32, i32, vp]),
         "mm_dispatch_multi": (i32, [C.POINTER(vp), i32, i32, i32, C.POINTER(vp)]),
         "mm_synchronize": (i32, [vp]),

@@ -49,6 +49,8 @@ struct mm_ctx {
     cudaExternalMemory_t ext_mem = nullptr;
     cudaMipmappedArray_t ext_mip = nullptr;
     cudaSurfaceObject_t surf = 0;
+    void *ext_linear = nullptr;    // mm_bind_output_external_buffer_fd: imported memory mapped as a linear buffer
+    cudaExternalSemaphore_t sems[8] = {};   // mm_import_semaphore_fd
     float *mirror = nullptr;       // set only for the duration of one mm_render_to_host dispatch
     float *host_mirror = nullptr;  // mm_bind_host_mirror: device view of a page-locked host frame every dispatch also stores into
     uint32_t *counters = nullptr;
@@ -60,6 +62,7 @@ struct mm_ctx {
     float *post_plane = nullptr;   // god-ray alpha plane of mm_post_chain
     size_t post_plane_bytes = 0;
     int lanes_per_ray = 0;         // mm_set_lanes_per_ray: 0 = chosen per dispatch, 1, 2, 4, 8
+    int arith = MM_ARITH_IEEE;     // mm_set_arithmetic: one rounding per operator, or the contracted (fused multiply-add) definition
     int scheduler = MM_SCHED_AUTO; // mm_set_scheduler: static grid (K1) or persistent warps with a dynamic queue (K1p)
     int refill = 32;               // K1p: dead lanes that trigger a refill (32 = a whole tile at a time)
     unsigned *queue = nullptr;     // K1p work-queue counter (device)
@@ -81,7 +84,10 @@ static int fail(mm_ctx *c, int code, const char *fmt, ...) {
 #define CU(call)                                                                                    \
     do {                                                                                            \
         cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+        if (e_ != cudaSuccess) {                                                                    \
+            cudaGetLastError();   /* a reported error must not resurface in a later, unrelated call */ \
+            return fail(ctx, MM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));                 \
+        }                                                                                           \
     } while (0)
 
 #ifndef MM_SPLIT_WAVES
@@ -139,6 +145,7 @@ static void free_slot(TexSlot &s) {
 static void release_output(mm_ctx *ctx) {
     if (ctx->surf) { cudaDestroySurfaceObject(ctx->surf); ctx->surf = 0; }
     if (ctx->ext_mip) { cudaFreeMipmappedArray(ctx->ext_mip); ctx->ext_mip = nullptr; }
+    if (ctx->ext_linear) { cudaFree(ctx->ext_linear); ctx->ext_linear = nullptr; }
     if (ctx->ext_mem) { cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr; }
     if (ctx->own_out) { cudaFree(ctx->own_out); ctx->own_out = nullptr; }
     if (ctx->counters) { cudaFree(ctx->counters); ctx->counters = nullptr; }
@@ -155,6 +162,7 @@ int mm_destroy(mm_ctx *ctx) {
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->post_plane) cudaFree(ctx->post_plane);
     if (ctx->queue) cudaFree(ctx->queue);
+    for (auto &sem : ctx->sems) if (sem) { cudaDestroyExternalSemaphore(sem); sem = nullptr; }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -367,6 +375,96 @@ int mm_bind_output_external_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, int w, i
     return size_counters(ctx);
 }
 
+// The same import for memory the engine laid out LINEARLY (a VkBuffer, or a VkImage created with VK_IMAGE_TILING_LINEAR whose row
+// pitch the engine reads from vkGetImageSubresourceLayout): mapped as a plain device buffer and written with ordinary stores, so
+// everything that works on mm_bind_output_linear (peer stores, host mirror, reprojection) works on it.  Also the one interop path
+// that can be exercised without a Vulkan loader: CUDA's own virtual-memory allocations export POSIX fds (tests/test_interop_gpu.py).
+int mm_bind_output_external_buffer_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, size_t offset_bytes, size_t pitch_bytes, int w, int h) {
+    if (!ctx) return MM_ERR_ARG;
+    if (fd < 0 || w <= 0 || h <= 0 || pitch_bytes < (size_t)w * 16 || (pitch_bytes & 15) || (offset_bytes & 15) ||
+        alloc_bytes < offset_bytes + pitch_bytes * (size_t)(h - 1) + (size_t)w * 16)
+        return fail(ctx, MM_ERR_ARG, "mm_bind_output_external_buffer_fd: bad arguments (16-byte aligned offset and pitch >= 16*w inside the allocation)");
+    CU(cudaSetDevice(ctx->device));
+    release_output(ctx);
+    cudaExternalMemoryHandleDesc hd = {};
+    hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+    hd.handle.fd = fd;
+    hd.size = alloc_bytes;
+    CU(cudaImportExternalMemory(&ctx->ext_mem, &hd));          // on success CUDA owns the fd
+    cudaExternalMemoryBufferDesc bd = {};
+    bd.offset = offset_bytes;
+    bd.size = alloc_bytes - offset_bytes;
+    cudaError_t e = cudaExternalMemoryGetMappedBuffer(&ctx->ext_linear, ctx->ext_mem, &bd);
+    if (e != cudaSuccess) {
+        cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr;
+        return fail(ctx, MM_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e));
+    }
+    ctx->out = static_cast<float *>(ctx->ext_linear); ctx->pitch = pitch_bytes; ctx->W = w; ctx->H = h;
+    return size_counters(ctx);
+}
+
+// ---- synchronisation with the engine's queues.  The reference submits its compute command buffer with no fence or semaphore at all
+// (VulkanApplication.cpp:168-177, vkQueueSubmit(computeQueue, 1, &submitInfo, VK_NULL_HANDLE)) and relies on vkQueueWaitIdle per frame;
+// a CUDA producer needs the ordering made explicit.  The engine exports a VkSemaphore (VK_EXTERNAL_SEMAPHORE_HANDLE_TYPE_OPAQUE_FD_BIT,
+// binary, or a timeline semaphore) per direction; mm_wait_semaphore orders a stream behind the engine's last reader of the image,
+// mm_signal_semaphore lets the graphics submits wait for the march.  Up to 8 imported semaphores per context.
+int mm_import_semaphore_fd(mm_ctx *ctx, int fd, int timeline, int *slot_out) {
+    if (!ctx || !slot_out) return MM_ERR_ARG;
+    if (fd < 0) return fail(ctx, MM_ERR_ARG, "mm_import_semaphore_fd: bad fd");
+    CU(cudaSetDevice(ctx->device));
+    int slot = -1;
+    for (int i = 0; i < 8; i++) if (!ctx->sems[i]) { slot = i; break; }
+    if (slot < 0) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_import_semaphore_fd: all 8 semaphore slots are in use");
+    cudaExternalSemaphoreHandleDesc sd = {};
+    sd.type = timeline ? cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd : cudaExternalSemaphoreHandleTypeOpaqueFd;
+    sd.handle.fd = fd;
+    CU(cudaImportExternalSemaphore(&ctx->sems[slot], &sd));
+    *slot_out = slot;
+    return MM_OK;
+}
+
+static int semaphore_op(mm_ctx *ctx, int slot, uint64_t value, void *stream_v, bool signal) {
+    if (!ctx) return MM_ERR_ARG;
+    if (slot < 0 || slot >= 8 || !ctx->sems[slot]) return fail(ctx, MM_ERR_STATE, "semaphore slot %d holds no imported semaphore", slot);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : ctx->stream;
+    if (signal) {
+        cudaExternalSemaphoreSignalParams sp = {};
+        sp.params.fence.value = value;                          // ignored by binary semaphores
+        CU(cudaSignalExternalSemaphoresAsync(&ctx->sems[slot], &sp, 1, stream));
+    } else {
+        cudaExternalSemaphoreWaitParams wp = {};
+        wp.params.fence.value = value;
+        CU(cudaWaitExternalSemaphoresAsync(&ctx->sems[slot], &wp, 1, stream));
+    }
+    return MM_OK;
+}
+int mm_signal_semaphore(mm_ctx *ctx, int slot, uint64_t value, void *stream) { return semaphore_op(ctx, slot, value, stream, true); }
+int mm_wait_semaphore(mm_ctx *ctx, int slot, uint64_t value, void *stream) { return semaphore_op(ctx, slot, value, stream, false); }
+int mm_release_semaphore(mm_ctx *ctx, int slot) {
+    if (!ctx) return MM_ERR_ARG;
+    if (slot < 0 || slot >= 8 || !ctx->sems[slot]) return fail(ctx, MM_ERR_STATE, "semaphore slot %d holds no imported semaphore", slot);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDestroyExternalSemaphore(ctx->sems[slot]));
+    ctx->sems[slot] = nullptr;
+    return MM_OK;
+}
+
+// Peer access for several contexts of ONE process (mm_dispatch_multi): lets `ctx`'s kernels store into memory that lives on
+// `peer`'s device.  (Across processes the CUDA-IPC open enables it; within a process nothing does it implicitly.)
+int mm_enable_peer(mm_ctx *ctx, mm_ctx *peer) {
+    if (!ctx || !peer) return MM_ERR_ARG;
+    if (ctx->device == peer->device) return MM_OK;
+    CU(cudaSetDevice(ctx->device));
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    if (!can) return fail(ctx, MM_ERR_UNSUPPORTED, "device %d cannot access device %d", ctx->device, peer->device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    if (e != cudaSuccess) return fail(ctx, MM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer->device, cudaGetErrorString(e));
+    return MM_OK;
+}
+
 // One frame sharded over n contexts of ONE process (one per GPU, or several on one GPU): context i marches partition i of n.  The
 // contexts' output bindings decide where the pixels land (the same image, mapped into every device, assembles the frame in place).
 int mm_dispatch_multi(mm_ctx **ctxs, int n, int mode, int row_block, void **streams) {
@@ -400,6 +498,13 @@ int mm_set_scheduler(mm_ctx *ctx, int scheduler, int refill_lanes) {
     return MM_OK;
 }
 
+int mm_set_arithmetic(mm_ctx *ctx, int arith) {
+    if (!ctx) return MM_ERR_ARG;
+    if (arith != MM_ARITH_IEEE && arith != MM_ARITH_FMA) return fail(ctx, MM_ERR_ARG, "mm_set_arithmetic: unknown definition %d", arith);
+    ctx->arith = arith;
+    return MM_OK;
+}
+
 int mm_set_filter_mode(mm_ctx *ctx, int filter) {
     if (!ctx) return MM_ERR_ARG;
     if (filter < MM_FILTER_EXACT || filter > MM_FILTER_HYBRID) return fail(ctx, MM_ERR_ARG, "mm_set_filter_mode: unknown mode %d", filter);
@@ -408,12 +513,18 @@ int mm_set_filter_mode(mm_ctx *ctx, int filter) {
 }
 
 // CC:392-401: samples[i] = mat3(sun.directionBasis) * s_i, column-major, ((c0*x)+(c1*y))+(c2*z) per
-// component, binary32, no contraction (this file's host code is built with -ffp-contract=off).
-static void light_cone_samples(const float *sun, float out[18]) {
+// component, binary32, no contraction (this file's host code is built with -ffp-contract=off); under the contracted
+// definition fma(c2, z, fma(c0, x, RN(c1*y))) (oracle/glsl_env_fma.h).
+static void light_cone_samples(const float *sun, float out[18], int arith) {
     static const float sv[6][3] = {{0.f, 0.6f, 0.f}, {0.f, 0.5f, 0.05f}, {0.1f, 0.75f, 0.f}, {0.2f, 2.5f, 0.3f}, {0.f, 6.f, 0.f}, {-0.1f, 1.f, -0.2f}};
     const float *c0 = sun + 12, *c1 = sun + 16, *c2 = sun + 20;
     for (int i = 0; i < 6; i++)
         for (int r = 0; r < 3; r++) {
+            if (arith == MM_ARITH_FMA) {
+                volatile float b = c1[r] * sv[i][1];
+                out[3 * i + r] = fmaf(c2[r], sv[i][2], fmaf(c0[r], sv[i][0], b));
+                continue;
+            }
             volatile float a = c0[r] * sv[i][0], b = c1[r] * sv[i][1], c = c2[r] * sv[i][2];
             volatile float ab = a + b;
             out[3 * i + r] = ab + c;
@@ -508,7 +619,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     memcpy(p.cam, ctx->cam, sizeof p.cam);
     memcpy(p.sun, ctx->sun, sizeof p.sun);
     memcpy(p.sky, ctx->sky, sizeof p.sky);
-    light_cone_samples(ctx->sun, p.light);
+    light_cone_samples(ctx->sun, p.light, ctx->arith);
     for (int i = 0; i < TEX_COUNT; i++) {
         const TexSlot &s = ctx->tex[i];
         p.tex[i].pairs = s.pairs; p.tex[i].obj = s.obj;
@@ -568,7 +679,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         CU(cudaMemsetAsync(ctx->queue, 0, 2 * sizeof(unsigned), stream));
     }
     CU(cudaEventRecord(ctx->ev0, stream));
-    CU(launch_cloud_march(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
+    CU((ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march)(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
     CU(cudaEventRecord(ctx->ev1, stream));
     ctx->timed = true;
     return MM_OK;
@@ -974,7 +1085,7 @@ int mm_det_pow(mm_ctx *ctx, const float *x, const float *y, int n, float *out) {
     CU(cudaMalloc(&d, (size_t)n * 12 + 16));
     cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = launch_det_pow(d, d + n, n, d + 2 * (size_t)n, ctx->stream);
+    if (e == cudaSuccess) e = (ctx->arith == MM_ARITH_FMA ? launch_det_pow_fma : launch_det_pow)(d, d + n, n, d + 2 * (size_t)n, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d);

@@ -109,6 +109,9 @@ cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
 // persistent_blocks > 0: K1p with that many 128-thread blocks (lanes_per_ray must be 1, p.queue zeroed on `stream`); refill 32/16/8
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, int lanes_per_ray, int persistent_blocks, int refill, cudaStream_t stream);
 int persistent_blocks_per_sm(int filter);
+// the same kernels built under the contracted arithmetic definition (cloud_march_fma.cu)
+cudaError_t launch_cloud_march_fma(const MarchParams &p, int filter, int lanes_per_ray, int persistent_blocks, int refill, cudaStream_t stream);
+cudaError_t launch_det_pow_fma(const float *x, const float *y, int n, float *out, cudaStream_t stream);
 void march_block_shape(int lanes_per_ray, int *block_w, int *block_h);   // pixels per block of the variant that will run
 cudaError_t launch_sample_probe(const TexDev &t, int is3d, int placement_layout, int filter, const float *uvw, int n, float4 *out, cudaStream_t stream);
 cudaError_t launch_tex_peak(cudaTextureObject_t obj, int is3d, int width, int iters, int blocks, float4 *sink, cudaStream_t stream);

@@ -130,6 +130,29 @@ class ComputeShader:
         self._check(self._lib.mm_bind_output_linear(self._ctx, C.c_void_p(int(device_ptr)), pitch, self.width, self.height))
         self.out_ptr, self.out_pitch = int(device_ptr), pitch
 
+    def bindOutputExternalBufferFd(self, fd, alloc_bytes, offset_bytes=0, pitch_bytes=None):
+        """external (Vulkan-exported, linearly laid out) memory as the output image; the library owns the fd on success"""
+        pitch = pitch_bytes or self.width * 16
+        self._check(self._lib.mm_bind_output_external_buffer_fd(self._ctx, int(fd), alloc_bytes, offset_bytes, pitch, self.width, self.height))
+        self.out_ptr, self.out_pitch = None, pitch
+
+    def importSemaphoreFd(self, fd, timeline=False):
+        slot = C.c_int()
+        self._check(self._lib.mm_import_semaphore_fd(self._ctx, int(fd), int(timeline), C.byref(slot)))
+        return slot.value
+
+    def waitSemaphore(self, slot, value=0, stream=None):
+        self._check(self._lib.mm_wait_semaphore(self._ctx, slot, value, self._stream(stream)))
+
+    def signalSemaphore(self, slot, value=0, stream=None):
+        self._check(self._lib.mm_signal_semaphore(self._ctx, slot, value, self._stream(stream)))
+
+    def releaseSemaphore(self, slot):
+        self._check(self._lib.mm_release_semaphore(self._ctx, slot))
+
+    def enablePeer(self, other):
+        self._check(self._lib.mm_enable_peer(self._ctx, other._ctx))
+
     # ---- host frame shared by several ranks: every dispatch also stores its pixels there (D2H fused into the kernel)
     def hostRegister(self, array):
         self._check(self._lib.mm_host_register(self._ctx, _ptr(array), array.nbytes))
@@ -172,6 +195,10 @@ class ComputeShader:
 
     def setFilterMode(self, mode):
         self._check(self._lib.mm_set_filter_mode(self._ctx, mode))
+
+    def setArithmetic(self, arith):
+        """MM_ARITH_IEEE (default: one rounding per operator) or MM_ARITH_FMA (the lexical contraction rule); a different DEFINITION"""
+        self._check(self._lib.mm_set_arithmetic(self._ctx, arith))
 
     def setLanesPerRay(self, lanes):
         """0 = per dispatch (default), 1, 2, 4, 8: scheduling only, results are identical"""

@@ -70,6 +70,7 @@ public:
 
     void setFilterMode(int mode) { check(mm_set_filter_mode(ctx_, mode)); }
     void setLanesPerRay(int lanes) { check(mm_set_lanes_per_ray(ctx_, lanes)); }     // scheduling only; 0 = per dispatch
+    void setArithmetic(int arith) { check(mm_set_arithmetic(ctx_, arith)); }          // MM_ARITH_IEEE (default) / MM_ARITH_FMA
     void setScheduler(int scheduler, int refillLanes = 0) { check(mm_set_scheduler(ctx_, scheduler, refillLanes)); }   // scheduling only
 
     // ReprojectShader: previous image (descriptor set 1) -> bound output, then dispatch(MM_PHASE16) re-marches 1/16 of it

@@ -16,6 +16,7 @@ OM_TEX_PLACEMENT, OM_TEX_NIGHTSKY, OM_TEX_CURL, OM_TEX_LOWRES, OM_TEX_HIRES = ra
 OM_FILTER_FP32, OM_FILTER_FIX8, OM_FILTER_TEXUNIT = 0, 1, 2
 OM_POW_DET, OM_POW_LIBM = 0, 1
 OM_FULL, OM_PHASE16 = 0, 1
+OM_ARITH_IEEE, OM_ARITH_FMA = 0, 1
 
 _lib = None
 
@@ -30,10 +31,11 @@ def lib():
         l.om_scene_set_texture.argtypes = [vp, i32, vp, i32, i32, i32]
         l.om_scene_set_uniforms.argtypes = [vp, vp, vp, vp]
         l.om_scene_set_modes.argtypes = [vp, i32, i32]
+        l.om_scene_set_arith.argtypes = [vp, i32]
         l.om_march.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32]
         l.om_sample.argtypes = [vp, i32, i32, vp, i32, vp]
         l.om_tonemap_rgba8.argtypes = [vp, C.c_size_t, vp]
-        for name, n in (("om_det_powf", 2), ("om_hgPhase", 2), ("om_remap", 5), ("om_remapClamped", 5),
+        for name, n in (("om_det_powf", 2), ("om_det_powf_fma", 2), ("om_hgPhase", 2), ("om_remap", 5), ("om_remapClamped", 5),
                         ("om_cloudLayerDensity", 2), ("om_heightBiasCoverage", 2), ("om_curl_hash", 3)):
             fn = getattr(l, name)
             fn.restype, fn.argtypes = f32, [f32] * n
@@ -57,7 +59,7 @@ def _p(a):
 
 
 class Scene:
-    def __init__(self, assets, cam, sun, sky, filter_mode=OM_FILTER_FP32, pow_mode=OM_POW_DET, nightsky=None):
+    def __init__(self, assets, cam, sun, sky, filter_mode=OM_FILTER_FP32, pow_mode=OM_POW_DET, nightsky=None, arith=OM_ARITH_IEEE):
         self.l = lib()
         self.s = self.l.om_scene_create()
         self._keep = []
@@ -67,6 +69,7 @@ class Scene:
             self.set_texture(OM_TEX_NIGHTSKY, nightsky)
         self.set_uniforms(cam, sun, sky)
         self.set_modes(filter_mode, pow_mode)
+        assert self.l.om_scene_set_arith(self.s, arith) == 0
 
     def set_texture(self, slot, a):
         a = np.ascontiguousarray(a, np.uint8)

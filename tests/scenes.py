@@ -22,6 +22,11 @@ def load_assets():
     return out
 
 
+def shipped_night_sky():
+    """The star map the application binds, Textures/NightSky/nightSky_noOrange.png (VulkanApplication.cpp:255-256): 1920x1080 RGBA8."""
+    return np.load(os.path.join(ASSETS, "nightSky_noOrange.npz"))["rgba8"]
+
+
 def constant_placement(r, b, size=64):
     """BASELINE's 'coverage' knob realised as a placement texture (SURVEY finding 3): R = coverage, B = cloud type."""
     t = np.zeros((size, size, 4), np.uint8)

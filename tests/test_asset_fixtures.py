@@ -37,3 +37,5 @@ def test_fixtures_equal_the_reference_decoder_on_the_reference_files(assets):
         assert np.array_equal(load(TEX + f"3DTextures/lowResCloudShape/lowResCloud({i}).tga", (128, 128, 4)), assets["lowres"][i]), i
     for i in range(32):                                                                                    # :262
         assert np.array_equal(load(TEX + f"3DTextures/hiResCloudShape/hiResClouds ({i}).tga", (32, 32, 4)), assets["hires"][i]), i
+    import scenes
+    assert np.array_equal(load(TEX + "NightSky/nightSky_noOrange.png", (1080, 1920, 4)), scenes.shipped_night_sky())   # :255-256

@@ -301,7 +301,7 @@ def test_exact_divide_by_constant_is_the_ieee_quotient(mm):
         assert bad == 0, f"div_const(x, {c!r}) differs from x / {c!r} for {bad} dividends"
         which += 1
     cs.close()
-    assert len(seen) >= 13          # 10 constants + sqrt + rcp + remapClampedTo1
+    assert len(seen) >= 15          # 12 constants (incl. the 0.3 of `stepSize /= 0.3`) + sqrt + rcp + remapClampedTo1
 
 
 @pytest.mark.parametrize("name,mode", [("C2", "hw"), ("C3", "hw"), ("C2", "hybrid"), ("C2", "exact"), ("C3", "hybrid")])
@@ -519,3 +519,57 @@ def test_dispatch_multi_assembles_one_frame_from_several_contexts(mm, assets):
     for cs in shaders:
         cs.close()
     assert np.array_equal(img.view(np.uint32), full.view(np.uint32))
+
+
+@pytest.mark.parametrize("mode", ["hw", "exact"])
+def test_night_frame_with_the_shipped_star_map(mm, oracle, assets, mode):
+    """The night branch (CC:365-384, 491-493) with the star map the application binds: Textures/NightSky/nightSky_noOrange.png,
+    1920x1080 -- not a power of two, so REPEAT wraps by modulo in the FP32 sampler and through the 21-bit coordinate of the texture
+    unit model (VERDICT r1 missing 5: night was only tested with a synthetic 96x64 map)."""
+    night = scenes.shipped_night_sky()
+    assert night.shape == (1080, 1920, 4)
+    W, H = 480, 270
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H, elevation=0.75, time=40.0)
+    assert sc["sun"][5] < 0                                                   # sun.direction.y < 0: night
+    kfilter, ofilter = getattr(mm, _FILTERS[mode][0]), getattr(oracle, _FILTERS[mode][1])
+    ref, rcnt = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=ofilter, nightsky=night).march(W, H)
+    cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"], nightSky=night)
+    cs.allocOutput()
+    cs.enableCounters(True)
+    cs.setFilterMode(kfilter)
+    img = cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+    cnt = cs.readCounters()
+    cs.close()
+    rep = oracle.parity_report(ref, img, rcnt, cnt)
+    print("night, shipped star map,", mode, rep)
+    assert rep["counter_mismatch_pixels"] == 0 and rep["alpha_identical_frac"] == 1.0 and rep["max_abs_diff_8bit"] <= 1, rep
+    assert int(rcnt[..., 1].max()) > 0 and float(ref[..., :3].max()) > 0.0
+
+
+@pytest.mark.parametrize("name", ["C5", "C5b"])
+def test_native_8k_rows_against_the_oracle(mm, oracle, assets, name):
+    """BASELINE config 5 at its NATIVE 7680x4320: every 64th row of the frame against the oracle -- counters and alpha bit for bit,
+    RGBA8 within 1 -- next to the size-independent properties above.  C5b is the measured worst case."""
+    import torch
+    sc = scenes.make_scene(mm, name, assets)
+    W, H = sc["W"], sc["H"]
+    rows = np.arange(0, H, 64)
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=oracle.OM_FILTER_TEXUNIT)
+    ref, rcnt = S.march(W, H, row_begin=0, row_stride=64, row_block=1)
+    cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+    out = torch.empty((H, W, 4), dtype=torch.float32, device="cuda")
+    cs.bindOutput(out.data_ptr())
+    cs.enableCounters(True)
+    cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+    cs.dispatch(mm.MM_FULL)
+    cs.synchronize()
+    img = out[::64].cpu().numpy()
+    cnt = cs.readCounters()[::64]
+    cs.close()
+    rep = oracle.parity_report(ref[rows], img, rcnt[rows], cnt)
+    print(name, "native 8K, every 64th row", rep)
+    assert rep["branch_flip_pixels"] == 0 and rep["counter_mismatch_pixels"] == 0 and rep["alpha_identical_frac"] == 1.0
+    assert rep["max_abs_diff_8bit"] <= 1 and rep["frac_within_1"] == 1.0
+    assert int(rcnt[rows][..., 0].sum()) > 1000000

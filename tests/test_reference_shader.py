@@ -25,16 +25,21 @@ class _SamplerCtx(C.Structure):
     _fields_ = [("scene", C.c_void_p), ("filter", C.c_int)]
 
 
-def _run_reference_shader(oracle, S, filt, sc, ids):
-    ref = C.CDLL(REF_CC)
-    ref.ref_cc_run.argtypes = [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+REF_CC_FMA = os.path.join(os.path.dirname(REF_CC), "libref_cc_fma.so")
+
+
+def _run_reference_shader(oracle, S, filt, sc, ids, arith="ieee"):
+    """arith "fma": the same shader text compiled in glsl_env_fma.h, whose operators apply the lexical contraction rule"""
+    lib = C.CDLL(REF_CC_FMA if arith == "fma" else REF_CC)
+    ref_cc_run = lib.ref_cc_fma_run if arith == "fma" else lib.ref_cc_run
+    ref_cc_run.argtypes = [C.c_void_p] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     out = np.full((1080, 1920, 4), -7.0, np.float32)
     written = np.zeros((1080, 1920), np.uint8)
     fetches = (C.c_ulonglong * 2)()
     ctx = _SamplerCtx(S.s, filt)
     cam, sun, sky = (np.ascontiguousarray(sc[k], np.float32) for k in ("cam", "sun", "sky"))
     ids = np.ascontiguousarray(ids, np.uint32)
-    rc = ref.ref_cc_run(oracle._p(cam), oracle._p(sun), oracle._p(sky), C.cast(oracle.lib().om_sample_callback, C.c_void_p), C.byref(ctx),
+    rc = ref_cc_run(oracle._p(cam), oracle._p(sun), oracle._p(sky), C.cast(oracle.lib().om_sample_callback, C.c_void_p), C.byref(ctx),
                         oracle._p(ids), len(ids), oracle._p(out), oracle._p(written), fetches)
     assert rc == 0
     return out, written.astype(bool), (int(fetches[0]), int(fetches[1]))
@@ -45,19 +50,23 @@ CASES = [("C1", 5, "fp32", {}), ("C3", 0, "fp32", {}), ("C5b", 15, "fp32", {}), 
          ("C1", 11, "texunit", {}), ("C1", 2, "texunit", dict(elevation=0.9, yaw=0.7, pitch=-0.6))]
 
 
+@pytest.mark.parametrize("arith", ["ieee", "fma"])
 @pytest.mark.parametrize("name,phase,sampler,over", CASES)
-def test_oracle_equals_the_reference_shader_text(mm, oracle, assets, name, phase, sampler, over):
+def test_oracle_equals_the_reference_shader_text(mm, oracle, assets, name, phase, sampler, over, arith):
+    """Both arithmetic definitions: one rounding per operator (cloud_march_oracle.c vs glsl_env.h) and the lexical fused-multiply-add
+    rule (cloud_march_oracle_fma.c, restated by hand, vs glsl_env_fma.h, which applies it mechanically to the shader text)."""
     W, H = 1920, 1080                                  # the shader hard-codes its extent (CC:283-285)
     sc = scenes.make_scene(mm, name, assets, W=W, H=H, pixel_phase=phase, **over)
     night = scenes.synthetic_night_sky() if sc["sun"][5] < 0 else None
     filt = oracle.OM_FILTER_TEXUNIT if sampler == "texunit" else oracle.OM_FILTER_FP32
     # libm pow on both sides: the shader's pow() is the language's; the oracle's deterministic pow is pinned separately
-    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=filt, pow_mode=oracle.OM_POW_LIBM, nightsky=night)
+    S = oracle.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=filt, pow_mode=oracle.OM_POW_LIBM, nightsky=night,
+                     arith=oracle.OM_ARITH_FMA if arith == "fma" else oracle.OM_ARITH_IEEE)
     # one reference dispatch (phase `phase`), ten 4-row bands of the frame: 4800 rays from top to below the horizon
     want, wcnt = S.march(W, H, mode=oracle.OM_PHASE16, row_begin=0, row_stride=27, row_block=4, out=np.full((H, W, 4), -7.0, np.float32))
     ys, xs = np.nonzero((want != -7.0).any(axis=-1))
     assert len(ys) == 4800 and (xs % 4 == phase % 4).all() and (ys % 4 == phase // 4).all()
-    got, written, fetches = _run_reference_shader(oracle, S, filt, sc, np.stack([xs // 4, ys // 4], 1))
+    got, written, fetches = _run_reference_shader(oracle, S, filt, sc, np.stack([xs // 4, ys // 4], 1), arith)
     assert np.array_equal(written, (want != -7.0).any(axis=-1)), "the shader wrote a different set of pixels"
     bad = (got.view(np.uint32) != want.view(np.uint32)).any(axis=-1)
     assert not bad.any(), (int(bad.sum()), got[bad][:3], want[bad][:3])

@@ -28,9 +28,10 @@ def main():
     curl = rgba(REF + "CurlNoiseFBM.tga")
     curl_png = rgba(REF + "CurlNoiseFBM.png")
     assert (curl[..., :3] == curl_png[..., :3]).all()
+    night = rgba(REF + "NightSky/nightSky_noOrange.png")          # the star map the app binds (VulkanApplication.cpp:255-256): 1920x1080, not a power of two
     man = {}
     for name, arr in [("lowResCloudShape", low), ("hiResCloudShape", hi),
-                      ("CloudPlacement", placement), ("CurlNoiseFBM", curl)]:
+                      ("CloudPlacement", placement), ("CurlNoiseFBM", curl), ("nightSky_noOrange", night)]:
         np.savez_compressed(os.path.join(OUT, name + ".npz"), rgba8=arr)
         man[name] = {"shape": list(arr.shape), "sha256": hashlib.sha256(arr.tobytes()).hexdigest()}
         print(name, arr.shape, man[name]["sha256"][:16])
