@@ -455,6 +455,11 @@ unsigned long long om_debug_stats[8];
 static int g_stats_on = 0;
 void om_debug_stats_enable(int on) { g_stats_on = on; if (on) memset(om_debug_stats, 0, sizeof om_debug_stats); }
 #define STAT(i) do { if (g_stats_on) { _Pragma("omp atomic") om_debug_stats[i]++; } } while (0)
+/* diagnostics: one record per cloudTest call {u, v, w of the low-res fetch, layerDensity, coverage = h^k, density at the gate, result, h}
+ * into a caller-owned buffer (single-threaded runs only; tools/prepass_bound.py measures what an occupancy prepass could prove) */
+static float *g_trace = NULL; static size_t g_trace_cap = 0, g_trace_n = 0;
+void om_debug_trace(float *buf, size_t capacity_records) { g_trace = buf; g_trace_cap = capacity_records; g_trace_n = 0; }
+size_t om_debug_trace_count(void) { return g_trace_n; }
 
 /* CC:231-253 (Q2: heightBiasCoverage called with swapped arguments) */
 static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
@@ -469,6 +474,12 @@ static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     cx->cnt->n3d++;
 
     float density = layerDensity * remapClampedf(dn[0], 0.3f, 1.0f, 0.0f, 1.0f);
+    float *trace = NULL;
+    if (g_trace && g_trace_n < g_trace_cap) {
+        trace = g_trace + 8 * g_trace_n++;
+        trace[0] = 0.00002f * pos.x; trace[1] = 0.00002f * pos.y; trace[2] = 0.00002f * pos.z; trace[3] = layerDensity;
+        trace[4] = heightBiasCoverage(s, relativeHeight, ominf(0.85f, ci[0])); trace[5] = density; trace[6] = 0.0f; trace[7] = relativeHeight;
+    }
     STAT(0);
     if (layerDensity == 0.0f) STAT(1);
     else if (density < 0.0001f) STAT(2);
@@ -480,6 +491,7 @@ static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     float erosion = ((0.625f * dn[1]) + (0.25f * dn[2])) + (0.125f * dn[3]);
     erosion = remapClampedf(erosion, coverage, 1.0f, 0.0f, 1.0f);
     density = remapClampedf(density, erosion, 1.0f, 0.0f, 1.0f);
+    if (trace) trace[6] = density;
     if (density > 0.0f) STAT(4); else STAT(3);
     if (k_is_one) STAT(5);
     return density;
