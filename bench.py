@@ -437,7 +437,8 @@ def main():
         def e2e_once():
             cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
             cs.dispatch(mm.MM_FULL, rank, world, args.row_block, stream=stream.cuda_stream)
-            barrier()                                   # every rank's stream has drained: the frame is complete in host memory
+            stream.synchronize()                        # this rank's pixels have landed in rank 0's image and in the host frame
+            hostframe.barrier()                         # ... and so have every other rank's: the frame is complete in host memory
         for _ in range(2):
             e2e_once()
         barrier()
@@ -453,7 +454,8 @@ def main():
         e2e = {"value": W * H / dt / 1e6, "unit": "Mpix/s", "ms_per_frame": dt * 1e3, "h2d_bytes_per_step": 328 * world,
                "d2h_bytes_per_step": W * H * 16, "host_frame_sha256": host_hash,
                "note": "uniform blocks from host on every rank; sharded march storing into rank 0's device image over NVLink and into one page-locked "
-                       "shared host frame over each GPU's PCIe link (device->host transfer fused into the kernels); barrier; wall clock"}
+                       "shared host frame over each GPU's PCIe link (device->host transfer fused into the kernels); per frame one stream synchronize per rank + a "
+                       "host-side shared-memory barrier of the ranks; wall clock"}
     else:
         host = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
         hnp = host.numpy()

@@ -537,7 +537,7 @@ static void light_cone_samples(const float *sun, float out[18], int arith) {
 // expensive as its LOWEST ray above it -- the block row that straddles the horizon holds the longest rays of the frame (250 loop
 // trips, ~0.45 ms as a dependent chain) and must start first, not with the free rows at the end (measured: that mistake cost the
 // rank owning it 15 % of its frame share).  Scheduling hint only.
-static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows, int block_h) {
+static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows, int block_h, bool free_rows_first = false) {
     const float *cam = p.cam;
     struct Key { float k; uint16_t i; };
     static thread_local Key keys[4096];
@@ -557,7 +557,10 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
     for (int b = 0; b < nblockrows; b++) {
         double y0 = elevation(b * block_h), y1 = elevation(b * block_h + block_h - 1);
         double hi = y0 > y1 ? y0 : y1, lo = y0 > y1 ? y1 : y0;
-        keys[b].k = hi < 0.0 ? 2.0f : (float)(lo > 0.0 ? lo : 0.0);  // ascending key = descending cost; all-below-horizon rows last
+        // ascending key = descending cost; all-below-horizon rows (free: CC:351-354 stores the sky colour and returns) last -- unless every
+        // pixel is also stored to HOST memory over PCIe (mm_render_to_host / mm_bind_host_mirror): then they go FIRST, so that their
+        // burst of stores (28 % of a C3 frame, ~0.7 ms of PCIe time at 4K) drains behind the march instead of after it
+        keys[b].k = hi < 0.0 ? (free_rows_first ? -1.0f : 2.0f) : (float)(lo > 0.0 ? lo : 0.0);
         keys[b].i = (uint16_t)b;
     }
     static const char *dbg = getenv("MM_DEBUG_ROW_ORDER");         // diagnostics: "identity" / "reverse" switch the cost order off
@@ -666,7 +669,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     if (persistent) { block_w = TILE_W; block_h = TILE_H; } else march_block_shape(lanes, &block_w, &block_h);
     int nblockrows = (p.owned_rows + block_h - 1) / block_h;
     if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
-    order_block_rows(p, p.block_row_order, nblockrows, block_h);
+    order_block_rows(p, p.block_row_order, nblockrows, block_h, p.mirror != nullptr);
     int persistent_blocks = 0;
     p.queue = nullptr; p.n_slots = 0; p.tiles_x = 0;
     if (persistent) {                                             // queue entries are pixel slots, 32 per 8x4 tile

@@ -65,17 +65,42 @@ class SharedFrame:
             self.remote_ptr = None
 
 
+class HostBarrier:
+    """Barrier between the processes of one node through shared memory: one int64 epoch per rank, a cache line apart, in a buffer
+    every process has mapped (at least world * 64 bytes, zero-initialised).  wait() publishes this rank's next epoch and spins until
+    every rank has published it.  x86 stores are ordered, and the ranks only ever increase their own slot."""
+
+    def __init__(self, buffer, rank, world, offset=0):
+        self.rank = rank
+        self._epochs = np.frombuffer(buffer, dtype=np.int64, count=world * 8, offset=offset)[::8]
+        self._epoch = 0
+
+    def wait(self):
+        self._epoch += 1
+        self._epochs[self.rank] = self._epoch
+        e = self._epochs
+        while int(e.min()) < self._epoch:
+            pass
+
+    def release(self):
+        self._epochs = None
+
+
 class SharedHostFrame:
     """The HOST copy of a sharded frame: one POSIX shared-memory mapping opened by every rank's process, page-locked and
     mapped into each rank's GPU.  Every rank's march kernel stores its pixels there as it finishes them (next to the store
     into rank 0's device image), so the device->host transfer of the frame runs over N PCIe links in parallel and overlaps
-    the march; after a barrier the frame is complete in `self.array` on every rank -- no gather, no copy."""
+    the march; after a barrier the frame is complete in `self.array` on every rank -- no gather, no copy.
+    The same mapping carries one epoch counter per rank behind the frame: `barrier()` is a host-side barrier between the ranks'
+    processes through that shared memory (a store and a spin on 8 cache lines), for the per-frame "every rank's stream has drained"
+    rendezvous -- no collective kernel, no device-wide synchronize."""
 
     def __init__(self, cs, rank, world, dist=None):
         import mmap
         import os
-        self.cs, self.rank = cs, rank
-        nbytes = cs.width * cs.height * 16
+        self.cs, self.rank, self.world = cs, rank, world
+        frame_bytes = cs.width * cs.height * 16
+        nbytes = frame_bytes + 4096
         name = [f"/dev/shm/marshmallow_frame_{os.getpid()}" if rank == 0 else None]
         if rank == 0:
             with open(name[0], "wb") as f:
@@ -85,7 +110,8 @@ class SharedHostFrame:
         self.path = name[0]
         self._f = open(self.path, "r+b")
         self._map = mmap.mmap(self._f.fileno(), nbytes)
-        self.array = np.frombuffer(self._map, dtype=np.float32).reshape(cs.height, cs.width, 4)
+        self.array = np.frombuffer(self._map, dtype=np.float32, count=cs.width * cs.height * 4).reshape(cs.height, cs.width, 4)
+        self._barrier = HostBarrier(self._map, rank, world, offset=frame_bytes)
         cs.hostRegister(self.array)
         cs.bindHostMirror(self.array)
         if world > 1:
@@ -93,11 +119,16 @@ class SharedHostFrame:
         if rank == 0:
             os.unlink(self.path)
 
+    def barrier(self):
+        """host-side barrier of the ranks' processes (each must have drained its own stream first)"""
+        self._barrier.wait()
+
     def close(self):
         if self.array is not None:
             self.cs.bindHostMirror(None)
             self.cs.hostUnregister(self.array)
             self.array = None
+            self._barrier.release()
             try:
                 self._map.close()
             except BufferError:           # a caller still holds a view of the frame; the mapping goes with its last reference

@@ -114,3 +114,42 @@ def test_handle_exchange_over_gloo_world_size_2(tmp_path):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def _barrier_worker(path, rank, world, rounds, q):
+    import mmap
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import _pkg
+    mg = _pkg.load_package().multigpu
+    f = open(path, "r+b")
+    m = mmap.mmap(f.fileno(), 4096)
+    b = mg.HostBarrier(m, rank, world, offset=1024)
+    log = np.frombuffer(m, dtype=np.int64, count=world, offset=0)
+    ok = True
+    for r in range(1, rounds + 1):
+        log[rank] = r                      # "my part of frame r is in the shared frame"
+        b.wait()
+        ok = ok and bool((log >= r).all())  # after the barrier every rank's part of frame r is visible
+        b.wait()                           # nobody starts frame r + 1 before everybody has checked frame r
+    b.release()
+    del log
+    q.put((rank, ok))
+
+
+def test_host_barrier_orders_the_ranks(tmp_path):
+    """multigpu.HostBarrier: the shared-memory rendezvous the sharded end-to-end path uses once per frame instead of a collective."""
+    import multiprocessing as mp
+    path = str(tmp_path / "barrier.bin")
+    with open(path, "wb") as f:
+        f.truncate(4096)
+    world, rounds = 3, 200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_barrier_worker, args=(path, r, world, rounds, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=30)
+    assert res == [(r, True) for r in range(world)]

@@ -16,18 +16,21 @@ cs.allocOutput()
 # K1s (2, 4, 8 lanes per ray), with and without counters, in the three sampler modes
 variants = [(1, mm.MM_SCHED_STATIC, 0), (1, mm.MM_SCHED_PERSISTENT, 32), (1, mm.MM_SCHED_PERSISTENT, 16), (1, mm.MM_SCHED_PERSISTENT, 8),
             (2, mm.MM_SCHED_AUTO, 0), (4, mm.MM_SCHED_AUTO, 0), (8, mm.MM_SCHED_AUTO, 0)]
-for counters in (False, True):
-    cs.enableCounters(counters)
-    for mode in (mm.MM_FILTER_EXACT, mm.MM_FILTER_HW, mm.MM_FILTER_HYBRID):
-        cs.setFilterMode(mode)
-        for lanes, sched, refill in variants:
-            cs.setLanesPerRay(lanes)
-            cs.setScheduler(sched, refill)
-            cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
-            cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sc["sun"])
-            cs.dispatch(mm.MM_PHASE16)
-            cs.dispatch(mm.MM_FULL, 1, 3, 2)
-            cs.synchronize()
+for arith in (mm.MM_ARITH_IEEE, mm.MM_ARITH_FMA):          # both builds of the march (cloud_march.cu, cloud_march_fma.cu)
+    cs.setArithmetic(arith)
+    for counters in (False, True):
+        cs.enableCounters(counters)
+        for mode in (mm.MM_FILTER_EXACT, mm.MM_FILTER_HW, mm.MM_FILTER_HYBRID):
+            cs.setFilterMode(mode)
+            for lanes, sched, refill in variants:
+                cs.setLanesPerRay(lanes)
+                cs.setScheduler(sched, refill)
+                cs.renderToHost(sc["cam"], sc["sky"], sc["sun"])
+                cs.updateUniformBuffers(sc["cam"], sc["cam"], sc["sky"], sc["sun"])
+                cs.dispatch(mm.MM_PHASE16)
+                cs.dispatch(mm.MM_FULL, 1, 3, 2)
+                cs.synchronize()
+cs.setArithmetic(mm.MM_ARITH_IEEE)
 cs.setLanesPerRay(0)
 cs.setScheduler(mm.MM_SCHED_AUTO, 0)
 cs.tonemapRGBA8()
