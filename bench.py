@@ -606,7 +606,8 @@ def main():
         # ---- scheduler variants on the same workload (scheduling only; frames are bit-identical, tests/test_scheduler_gpu.py)
         schedv = {}
         for label, sv, rf in (("static_grid_K1", mm.MM_SCHED_STATIC, 0), ("persistent_K1p_tile", mm.MM_SCHED_PERSISTENT, 32),
-                              ("persistent_K1p_refill16", mm.MM_SCHED_PERSISTENT, 16), ("persistent_K1p_refill8", mm.MM_SCHED_PERSISTENT, 8)):
+                              ("persistent_K1p_refill16", mm.MM_SCHED_PERSISTENT, 16), ("persistent_K1p_refill8", mm.MM_SCHED_PERSISTENT, 8),
+                              ("packed_two_rays_per_thread_K1x2", mm.MM_SCHED_PACKED, 0)):
             cs.setScheduler(sv, rf)
             schedv[label] = time_frames(torch, mm, cs, stream, flush, max(3, K // 4))
         cs.setScheduler(sched, args.refill)

@@ -142,8 +142,10 @@ MM_API int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes);
  *   MM_SCHED_PERSISTENT  one resident wave of warps pulling 8x4 pixel tiles, most expensive first, from an atomic queue in device
  *                        memory; refill_lanes = 32 (or 0): a warp takes a new tile when all its rays are done; 16 / 8: as soon as
  *                        that many lanes hold finished rays, those lanes store their pixels and are refilled from the queue
+ *   MM_SCHED_PACKED      K1x2: static grid, TWO neighbouring rays per thread on packed FP32 instructions (FADD2 / FFMA2): every arithmetic
+ *                        instruction of the decision path serves both rays; texture-unit mode without counters (anything else runs K1)
  *   MM_SCHED_AUTO        (default) MM_SCHED_STATIC: measured at least as fast on every workload */
-enum mm_scheduler { MM_SCHED_AUTO = 0, MM_SCHED_STATIC = 1, MM_SCHED_PERSISTENT = 2 };
+enum mm_scheduler { MM_SCHED_AUTO = 0, MM_SCHED_STATIC = 1, MM_SCHED_PERSISTENT = 2, MM_SCHED_PACKED = 3 };
 MM_API int mm_set_scheduler(mm_ctx *ctx, int scheduler, int refill_lanes);
 MM_API int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_block, void *stream);
 /* one frame over n contexts of one process (one per GPU): context i marches partition i of n (row blocks of row_block rows) on

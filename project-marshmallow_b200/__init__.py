@@ -13,7 +13,7 @@ Layout:
 """
 from .capi import (  # noqa: F401
     MM_FULL, MM_PHASE16, MM_ROWS_SNAKE, MM_FILTER_EXACT, MM_FILTER_HW, MM_FILTER_HYBRID,
-    MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT, MM_ARITH_IEEE, MM_ARITH_FMA,
+    MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT, MM_SCHED_PACKED, MM_ARITH_IEEE, MM_ARITH_FMA,
     MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES,
     MarshmallowError, library_path, load_library, exported_symbols, host_sky, host_camera, plan_block_rows,
 )

@@ -15,7 +15,7 @@ HEADER = os.path.join(HERE, "..", "include", "marshmallow.h")
 MM_FULL, MM_PHASE16 = 0, 1
 MM_ROWS_SNAKE = 0x100
 MM_FILTER_EXACT, MM_FILTER_HW, MM_FILTER_HYBRID = 0, 1, 2
-MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT = 0, 1, 2
+MM_SCHED_AUTO, MM_SCHED_STATIC, MM_SCHED_PERSISTENT, MM_SCHED_PACKED = 0, 1, 2, 3
 MM_ARITH_IEEE, MM_ARITH_FMA = 0, 1
 MM_TEX_PLACEMENT, MM_TEX_NIGHTSKY, MM_TEX_CURL, MM_TEX_LOWRES, MM_TEX_HIRES = range(5)
 

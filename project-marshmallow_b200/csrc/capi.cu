@@ -488,7 +488,7 @@ int mm_set_lanes_per_ray(mm_ctx *ctx, int lanes) {
 
 int mm_set_scheduler(mm_ctx *ctx, int scheduler, int refill_lanes) {
     if (!ctx) return MM_ERR_ARG;
-    if (scheduler != MM_SCHED_AUTO && scheduler != MM_SCHED_STATIC && scheduler != MM_SCHED_PERSISTENT)
+    if (scheduler != MM_SCHED_AUTO && scheduler != MM_SCHED_STATIC && scheduler != MM_SCHED_PERSISTENT && scheduler != MM_SCHED_PACKED)
         return fail(ctx, MM_ERR_ARG, "mm_set_scheduler: unknown scheduler %d", scheduler);
     if (refill_lanes == 0) refill_lanes = 32;
     if (refill_lanes != 32 && refill_lanes != 16 && refill_lanes != 8)
@@ -665,6 +665,8 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     // K1p (persistent warps + dynamic queue) instead of the static grid: opt-in.  Measured on B200 (profiles/r02_scheduler_ab.txt):
     // equal to the static grid on whole frames (5.85 vs 5.82 ms at 4K), 2-11 % slower on the row shares of an 8-GPU frame
     const bool persistent = lanes == 1 && ctx->scheduler == MM_SCHED_PERSISTENT;
+    // K1x2 (two rays per thread on packed FP32): the texture-unit mode without diagnostic counters; anything else runs K1
+    const bool packed = lanes == 1 && ctx->scheduler == MM_SCHED_PACKED && ctx->filter == FILTER_HW && !p.counters;
     int block_w, block_h;
     if (persistent) { block_w = TILE_W; block_h = TILE_H; } else march_block_shape(lanes, &block_w, &block_h);
     int nblockrows = (p.owned_rows + block_h - 1) / block_h;
@@ -681,6 +683,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         persistent_blocks = (int)std::min(resident, (tiles + 3u) / 4u);
         CU(cudaMemsetAsync(ctx->queue, 0, 2 * sizeof(unsigned), stream));
     }
+    if (packed) persistent_blocks = -1;
     CU(cudaEventRecord(ctx->ev0, stream));
     CU((ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march)(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
     CU(cudaEventRecord(ctx->ev1, stream));

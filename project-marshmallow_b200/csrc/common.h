@@ -107,6 +107,7 @@ cudaError_t launch_cloud_shadow(const ShadowParams &p, int filter, cudaStream_t 
 
 cudaError_t launch_reproject(const ReprojectParams &p, cudaStream_t stream);
 // persistent_blocks > 0: K1p with that many 128-thread blocks (lanes_per_ray must be 1, p.queue zeroed on `stream`); refill 32/16/8
+// persistent_blocks < 0: K1x2, two rays per thread on packed FP32 (FILTER_HW, no counters, lanes_per_ray 1; block rows of 8)
 cudaError_t launch_cloud_march(const MarchParams &p, int filter, int lanes_per_ray, int persistent_blocks, int refill, cudaStream_t stream);
 int persistent_blocks_per_sm(int filter);
 // the same kernels built under the contracted arithmetic definition (cloud_march_fma.cu)

@@ -43,7 +43,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     r0, n = (int(x) for x in a.shard.split("/"))
     table = {"static": (1, mm.MM_SCHED_STATIC, 0), "tile": (1, mm.MM_SCHED_PERSISTENT, 32), "group": (1, mm.MM_SCHED_PERSISTENT, 128),
-             "refill16": (1, mm.MM_SCHED_PERSISTENT, 16), "refill8": (1, mm.MM_SCHED_PERSISTENT, 8),
+             "packed": (1, mm.MM_SCHED_PACKED, 0), "refill16": (1, mm.MM_SCHED_PERSISTENT, 16), "refill8": (1, mm.MM_SCHED_PERSISTENT, 8),
              "lanes2": (2, mm.MM_SCHED_AUTO, 0), "lanes4": (4, mm.MM_SCHED_AUTO, 0), "lanes8": (8, mm.MM_SCHED_AUTO, 0), "auto": (0, mm.MM_SCHED_AUTO, 0)}
     for name in a.variants.split(","):
         lanes, sched, refill = table[name]

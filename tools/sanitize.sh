@@ -14,7 +14,7 @@ cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc[
 cs.allocOutput()
 # every march kernel variant: K1 (static grid), K1p (persistent warps; a tile at a time, refill at 16 / 8 dead lanes) and
 # K1s (2, 4, 8 lanes per ray), with and without counters, in the three sampler modes
-variants = [(1, mm.MM_SCHED_STATIC, 0), (1, mm.MM_SCHED_PERSISTENT, 32), (1, mm.MM_SCHED_PERSISTENT, 16), (1, mm.MM_SCHED_PERSISTENT, 8),
+variants = [(1, mm.MM_SCHED_STATIC, 0), (1, mm.MM_SCHED_PACKED, 0), (1, mm.MM_SCHED_PERSISTENT, 32), (1, mm.MM_SCHED_PERSISTENT, 16), (1, mm.MM_SCHED_PERSISTENT, 8),
             (2, mm.MM_SCHED_AUTO, 0), (4, mm.MM_SCHED_AUTO, 0), (8, mm.MM_SCHED_AUTO, 0)]
 for arith in (mm.MM_ARITH_IEEE, mm.MM_ARITH_FMA):          # both builds of the march (cloud_march.cu, cloud_march_fma.cu)
     cs.setArithmetic(arith)
