@@ -659,12 +659,23 @@ def main():
                 k_rep.append(r_ms)
                 k_march.append(m_ms)
             cur, prev = prev, cur
+        # the same pass with a camera that MOVED since the previous frame (the case reprojection exists for): every pixel's ten taps
+        # select different source pixels, so the single-load path of K5 does not apply
+        cfg3 = scenes.CONFIGS[args.config]
+        moved = mm.host_camera((cfg3["pos"][0] - 3.0, cfg3["pos"][1], cfg3["pos"][2] - 2.0), cfg3["yaw"] - 0.004, cfg3["pitch"] + 0.002, 45.0, 1920.0 / 1080.0)
+        cad.updateUniformBuffers(sc["cam"], moved, sc["sky"], sc["sun"])
+        k_mov = []
+        for i in range(max(3, K // 2) + 1):
+            flush.fill_(1)
+            cad.dispatchReproject(stream=stream.cuda_stream)
+            if i:
+                k_mov.append(cad.lastKernelMs())
         torch.cuda.synchronize()
         cad.close()
         del ping, pong
         kr, km = sum(k_rep) / K, sum(k_march) / K
         extras["reference_cadence"] = {"ms_per_frame": kr + km, "frames_per_s": 1e3 / (kr + km), "reproject_kernel_ms": kr, "phase16_march_kernel_ms": km,
-                                       "launches_per_frame": 2,
+                                       "reproject_kernel_ms_moving_camera": sum(k_mov) / len(k_mov), "launches_per_frame": 2,
                                        "note": "reference cadence: reprojection of the previous image + one MM_PHASE16 dispatch (1/16 of the pixels marched), ping-pong images, "
                                                "L2 flushed between frames; ms_per_frame = sum of the two kernels' CUDA-event times"}
 

@@ -66,14 +66,34 @@ __global__ void __launch_bounds__(256) reproject_kernel(const __grid_constant__ 
     float oldV = (((-od.y) / tanH) * 0.5f) + 0.5f;                                           // :135-136
     float bvx = oldU - uvx, bvy = oldV - uvy;                                                // :138
 
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < 10; ++s) {                                                           // :142-147
+    // :142-147, ten taps along the motion vector.  The tap index is a monotonic function of the tap number (every operation of
+    // round((old - bv*k) * dim) is monotonic, k = s/9 - 0.5 increases with s), so when the FIRST and the LAST tap select the same
+    // source pixel all ten do: one load, and the ten ordered additions of the reference on that one value.  That is every pixel of
+    // a frame whose camera moved by less than a pixel over the blur span (a static camera in particular); otherwise the full loop.
+    auto tap_index = [&](int s, int &sx, int &sy) {
         float k = ((float)s / 9.0f) - 0.5f;
         float ix = roundf((oldU - (bvx * k)) * dimx), iy = roundf((oldV - (bvy * k)) * dimy);
-        int sx = clampi(to_int(ix), 0, P.W - 1), sy = clampi(to_int(iy), 0, P.H - 1);
-        float4 t = __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(P.src) + (size_t)sy * P.src_pitch) + sx);
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        sx = clampi(to_int(ix), 0, P.W - 1); sy = clampi(to_int(iy), 0, P.H - 1);
+    };
+    auto tap_load = [&](int sx, int sy) {
+        return __ldg(reinterpret_cast<const float4 *>(reinterpret_cast<const char *>(P.src) + (size_t)sy * P.src_pitch) + sx);
+    };
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int x0, y0, x9, y9;
+    tap_index(0, x0, y0);
+    tap_index(9, x9, y9);
+    if (x0 == x9 && y0 == y9) {
+        float4 t = tap_load(x0, y0);
+#pragma unroll
+        for (int s = 0; s < 10; ++s) { acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+    } else {
+#pragma unroll
+        for (int s = 0; s < 10; ++s) {
+            int sx, sy;
+            tap_index(s, sx, sy);
+            float4 t = tap_load(sx, sy);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
     }
     acc.x = acc.x / 10.0f; acc.y = acc.y / 10.0f; acc.z = acc.z / 10.0f;                      // :148
     int cx = clampi(to_int(roundf(oldU * dimx)), 0, P.W - 1), cy = clampi(to_int(roundf(oldV * dimy)), 0, P.H - 1);   // :150-151

@@ -70,3 +70,31 @@ def test_sharded_frame_is_byte_identical(tmp_path, world):
                           "--master-port", str(port), str(script)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert f"multigpu ok {world}" in out.stdout
+
+
+def test_dispatch_multi_over_two_devices_of_one_process(mm, assets):
+    """several GPUs driven by ONE process -- one context per device, mm_enable_peer, the same image bound in each,
+    mm_dispatch_multi -- must assemble the single-GPU frame bit for bit (without the peer call the second device's stores would fault)."""
+    import torch
+    import scenes
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H = 320, 187
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H)
+    tex = sc["textures"]
+    shaders = [mm.ComputeShader(d, (W, H), placement=tex["placement"], curl=tex["curl"], lowRes=tex["lowres"], hiRes=tex["hires"]) for d in (0, 1)]
+    ptr, pitch = shaders[0].allocOutput()
+    shaders[1].enablePeer(shaders[0])
+    shaders[1].bindOutput(ptr, pitch)
+    for cs in shaders:
+        cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+    mm.dispatchMulti(shaders, mm.MM_FULL, 8)
+    for cs in shaders:
+        cs.synchronize()
+    sharded = shaders[0].readOutput()
+    shaders[0].dispatch(mm.MM_FULL)
+    shaders[0].synchronize()
+    single = shaders[0].readOutput()
+    for cs in shaders:
+        cs.close()
+    assert np.array_equal(sharded.view(np.uint32), single.view(np.uint32))
