@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "libmarshmallow_b200.so")
+LIB = os.environ.get("MM_LIB_OUT") or os.path.join(HERE, "libmarshmallow_b200.so")      # MM_LIB_OUT: build a variant (with MM_NVCC_EXTRA) beside the product library
 DEMO = os.path.join(HERE, "frame_demo")
 CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/cloud_march_fma.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu", "csrc/reproject.cu", "csrc/post_chain.cu"]
 CPP_SOURCES = ["host/sky_camera.cpp"]
@@ -33,10 +33,11 @@ def build_library(force=False, verbose=False, ptxas_v=False):
     if not force and not _stale():
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    bdir = "build" if not os.environ.get("MM_LIB_OUT") else "build_" + os.path.splitext(os.path.basename(LIB))[0]
+    os.makedirs(os.path.join(HERE, bdir), exist_ok=True)
     procs = []
     for src in CU_SOURCES + CPP_SOURCES:
-        obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
+        obj = os.path.join(HERE, bdir, os.path.basename(src) + ".o")
         cmd = [NVCC] + ARCH + CFLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
@@ -52,6 +53,8 @@ def build_library(force=False, verbose=False, ptxas_v=False):
         raise RuntimeError("nvcc failed")
     cmd = [NVCC] + ARCH + ["-shared", "--cudart", "static", "-o", LIB] + objs
     subprocess.run(cmd, check=True)
+    if os.environ.get("MM_LIB_OUT"):
+        return LIB
     # the headless C++ host demo (host/frame_demo.cpp) over the C++ mirror classes
     subprocess.run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-o", DEMO, os.path.join(HERE, "host", "frame_demo.cpp"),
                     "-L" + HERE, "-lmarshmallow_b200", "-Wl,-rpath,$ORIGIN"], check=True)
