@@ -111,7 +111,7 @@ def test_dispatch_argument_checks(mm, assets):
         for begin, stride in ((2, 2), (5, 3), (1, 1)):
             with pytest.raises(mm.MarshmallowError):
                 cs.dispatch(mode, begin, stride, 2)
-    for bad in ((3, 0), (3, 40), (1, 7)):
+    for bad in ((9, 0), (2, 40), (1, 7)):
         with pytest.raises(mm.MarshmallowError):
             cs.setScheduler(*bad)
     cs.synchronize()
