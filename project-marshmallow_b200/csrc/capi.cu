@@ -36,6 +36,11 @@ struct mm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t side = nullptr;   // copy stream of the split end-to-end dispatch (forked from / joined to the dispatch stream)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool out_is_local = false;     // the bound linear image lives on this context's device (not a peer's)
+    float *e2e_scratch = nullptr;  // local staging image of the split end-to-end dispatch when the bound image is a peer's
+    size_t e2e_scratch_bytes = 0;
     bool timed = false;
     TexSlot tex[TEX_COUNT];
     float cam[40], cam_prev[40], sun[29], sky[13];
@@ -125,6 +130,9 @@ int mm_create(int device, mm_ctx **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->queue, 2 * sizeof(unsigned));
     if (e != cudaSuccess) {
         fail(nullptr, MM_ERR_CUDA, "mm_create: %s", cudaGetErrorString(e));
@@ -149,7 +157,7 @@ static void release_output(mm_ctx *ctx) {
     if (ctx->ext_mem) { cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr; }
     if (ctx->own_out) { cudaFree(ctx->own_out); ctx->own_out = nullptr; }
     if (ctx->counters) { cudaFree(ctx->counters); ctx->counters = nullptr; }
-    ctx->out = nullptr; ctx->pitch = 0; ctx->W = ctx->H = 0;
+    ctx->out = nullptr; ctx->pitch = 0; ctx->W = ctx->H = 0; ctx->out_is_local = false;
 }
 
 int mm_destroy(mm_ctx *ctx) {
@@ -162,9 +170,13 @@ int mm_destroy(mm_ctx *ctx) {
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->post_plane) cudaFree(ctx->post_plane);
     if (ctx->queue) cudaFree(ctx->queue);
+    if (ctx->e2e_scratch) cudaFree(ctx->e2e_scratch);
     for (auto &sem : ctx->sems) if (sem) { cudaDestroyExternalSemaphore(sem); sem = nullptr; }
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return MM_OK;
@@ -330,6 +342,11 @@ int mm_bind_output_linear(mm_ctx *ctx, float *dptr, size_t pitch, int w, int h) 
     CU(cudaSetDevice(ctx->device));
     release_output(ctx);
     ctx->out = dptr; ctx->pitch = pitch; ctx->W = w; ctx->H = h;
+    {   // a peer GPU's image (multi-GPU gather fused into the stores) must not be copied from by THIS context's copy engine
+        cudaPointerAttributes attr;
+        ctx->out_is_local = cudaPointerGetAttributes(&attr, dptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice && attr.device == ctx->device;
+        cudaGetLastError();
+    }
     return size_counters(ctx);
 }
 
@@ -339,7 +356,7 @@ int mm_alloc_output(mm_ctx *ctx, int w, int h, float **dptr_out, size_t *pitch_o
     CU(cudaSetDevice(ctx->device));
     release_output(ctx);
     CU(cudaMalloc(&ctx->own_out, (size_t)w * h * 16));
-    ctx->out = ctx->own_out; ctx->pitch = (size_t)w * 16; ctx->W = w; ctx->H = h;
+    ctx->out = ctx->own_out; ctx->pitch = (size_t)w * 16; ctx->W = w; ctx->H = h; ctx->out_is_local = true;
     if (dptr_out) *dptr_out = ctx->out;
     if (pitch_out) *pitch_out = ctx->pitch;
     return size_counters(ctx);
@@ -399,7 +416,7 @@ int mm_bind_output_external_buffer_fd(mm_ctx *ctx, int fd, size_t alloc_bytes, s
         cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr;
         return fail(ctx, MM_ERR_CUDA, "cudaExternalMemoryGetMappedBuffer: %s", cudaGetErrorString(e));
     }
-    ctx->out = static_cast<float *>(ctx->ext_linear); ctx->pitch = pitch_bytes; ctx->W = w; ctx->H = h;
+    ctx->out = static_cast<float *>(ctx->ext_linear); ctx->pitch = pitch_bytes; ctx->W = w; ctx->H = h; ctx->out_is_local = false;
     return size_counters(ctx);
 }
 
@@ -537,11 +554,12 @@ static void light_cone_samples(const float *sun, float out[18], int arith) {
 // expensive as its LOWEST ray above it -- the block row that straddles the horizon holds the longest rays of the frame (250 loop
 // trips, ~0.45 ms as a dependent chain) and must start first, not with the free rows at the end (measured: that mistake cost the
 // rank owning it 15 % of its frame share).  Scheduling hint only.
-static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows, int block_h, bool free_rows_first = false) {
+static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockrows, int block_h, bool free_rows_first = false, int *nfree_out = nullptr) {
     const float *cam = p.cam;
     struct Key { float k; uint16_t i; };
     static thread_local Key keys[4096];
     const int last_row = p.owned_rows - 1;
+    int nfree = 0;
     auto elevation = [&](int j) {                                  // rd.y of the middle-column ray of owned row j
         if (j > last_row) j = last_row;
         int py;
@@ -562,9 +580,11 @@ static void order_block_rows(const MarchParams &p, uint16_t *order, int nblockro
         // burst of stores (28 % of a C3 frame, ~0.7 ms of PCIe time at 4K) drains behind the march instead of after it
         keys[b].k = hi < 0.0 ? (free_rows_first ? -1.0f : 2.0f) : (float)(lo > 0.0 ? lo : 0.0);
         keys[b].i = (uint16_t)b;
+        if (hi < 0.0) nfree++;
     }
+    if (nfree_out) *nfree_out = nfree;
     static const char *dbg = getenv("MM_DEBUG_ROW_ORDER");         // diagnostics: "identity" / "reverse" switch the cost order off
-    if (dbg && dbg[0] == 'i') { for (int b = 0; b < nblockrows; b++) order[b] = (uint16_t)b; return; }
+    if (dbg && dbg[0] == 'i') { for (int b = 0; b < nblockrows; b++) order[b] = (uint16_t)b; if (nfree_out) *nfree_out = 0; return; }
     std::stable_sort(keys, keys + nblockrows, [](const Key &a, const Key &b) { return a.k < b.k; });
     for (int b = 0; b < nblockrows; b++) order[b] = keys[(dbg && dbg[0] == 'r') ? nblockrows - 1 - b : b].i;
 }
@@ -671,7 +691,9 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     if (persistent) { block_w = TILE_W; block_h = TILE_H; } else march_block_shape(lanes, &block_w, &block_h);
     int nblockrows = (p.owned_rows + block_h - 1) / block_h;
     if (nblockrows > 4096) return fail(ctx, MM_ERR_UNSUPPORTED, "mm_dispatch: too many rows per dispatch");
-    order_block_rows(p, p.block_row_order, nblockrows, block_h, p.mirror != nullptr);
+    int nfree = 0;
+    order_block_rows(p, p.block_row_order, nblockrows, block_h, p.mirror != nullptr, &nfree);
+    if (getenv("MM_DEBUG_ROW_ORDER")) nfree = 0;
     int persistent_blocks = 0;
     p.queue = nullptr; p.n_slots = 0; p.tiles_x = 0;
     if (persistent) {                                             // queue entries are pixel slots, 32 per 8x4 tile
@@ -684,6 +706,74 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
         CU(cudaMemsetAsync(ctx->queue, 0, 2 * sizeof(unsigned), stream));
     }
     if (packed) persistent_blocks = -1;
+    p.launch_block_rows = 0;
+    // End-to-end split.  A kernel's stores into mapped host memory top out near 21 GB/s on this platform, the copy engine reaches 55 GB/s
+    // (tools/e2e_probe.py): a 4K frame mirrored pixel by pixel is PCIe-bound (6.37 ms against 5.66 ms of march).  The rows below the
+    // horizon cost no march time and are 28 % of the C3 frame's bytes: they are marched FIRST in a launch of their own that does not
+    // mirror, then copied device -> host by the copy engine on a second stream while the rest of the frame marches and mirrors its own
+    // pixels.  When the bound image is a PEER's (ranks != 0 of a sharded frame) the copy engine must not read it -- that would go through the
+    // peer's engine and PCIe link -- so those rows are stored to the peer image and to a local staging image, and copied from there.
+    static const char *split_env = getenv("MM_E2E_SPLIT");         // diagnostics: "0" keeps every pixel on the kernel-store path
+    if (p.mirror && p.out && mode == MM_FULL && !persistent && nfree > 0 && !(split_env && split_env[0] == '0')) {
+        auto launch = ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march;
+        static thread_local MarchParams head;
+        head = p;
+        head.mirror = nullptr;
+        const char *copy_src = reinterpret_cast<const char *>(p.out);
+        size_t copy_pitch = p.pitch;
+        if (!ctx->out_is_local) {
+            const size_t need = (size_t)p.W * p.H * 16;
+            if (ctx->e2e_scratch_bytes < need) {
+                if (ctx->e2e_scratch) { CU(cudaFree(ctx->e2e_scratch)); ctx->e2e_scratch = nullptr; ctx->e2e_scratch_bytes = 0; }
+                CU(cudaMalloc(&ctx->e2e_scratch, need));
+                ctx->e2e_scratch_bytes = need;
+            }
+            head.mirror = ctx->e2e_scratch; head.mirror_pitch = (size_t)p.W * 16;
+            copy_src = reinterpret_cast<const char *>(ctx->e2e_scratch); copy_pitch = (size_t)p.W * 16;
+        }
+        head.launch_block_rows = nfree;                          // the free block rows lead the order when a mirror is bound
+        CU(cudaEventRecord(ctx->ev0, stream));
+        CU(launch(head, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
+        CU(cudaEventRecord(ctx->ev_fork, stream));
+        CU(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        if (nblockrows > nfree) {
+            memmove(p.block_row_order, p.block_row_order + nfree, sizeof(uint16_t) * (size_t)(nblockrows - nfree));
+            p.launch_block_rows = nblockrows - nfree;
+            CU(launch(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
+        }
+        // the free rows as runs of consecutive image rows -> one 2D copy per run
+        int run_y = -1, run_n = 0;
+        auto flush = [&]() -> cudaError_t {
+            if (run_n <= 0) return cudaSuccess;
+            cudaError_t e = cudaMemcpy2DAsync(reinterpret_cast<char *>(p.mirror) + (size_t)run_y * p.mirror_pitch, p.mirror_pitch,
+                                              copy_src + (size_t)run_y * copy_pitch, copy_pitch, (size_t)p.W * 16, (size_t)run_n,
+                                              cudaMemcpyDefault, ctx->side);
+            run_n = 0;
+            return e;
+        };
+        static thread_local int rows[4096 * 8];
+        int nrows = 0;
+        for (int i = 0; i < nfree; i++)
+            for (int r = 0; r < block_h; r++) {
+                int j = (int)head.block_row_order[i] * block_h + r;
+                if (j >= p.owned_rows) continue;
+                int k = j / row_block;
+                int py = owned_block(k, row_begin, row_stride, snake) * row_block + (j - k * row_block);
+                if (py < p.H && nrows < 4096 * 8) rows[nrows++] = py;
+            }
+        std::sort(rows, rows + nrows);
+        for (int i = 0; i < nrows; i++) {
+            if (run_n > 0 && rows[i] == run_y + run_n) { run_n++; continue; }
+            CU(flush());
+            run_y = rows[i]; run_n = 1;
+        }
+        CU(flush());
+        CU(cudaEventRecord(ctx->ev_join, ctx->side));
+        CU(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
+        CU(cudaEventRecord(ctx->ev1, stream));
+        ctx->timed = true;
+        return MM_OK;
+    }
     CU(cudaEventRecord(ctx->ev0, stream));
     CU((ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march)(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
     CU(cudaEventRecord(ctx->ev1, stream));

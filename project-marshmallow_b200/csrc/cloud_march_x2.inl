@@ -99,12 +99,11 @@ PF v3p pwindOffset(v3 windXYZ, float wz20, float timeOffset, f2 h) {
 
 struct Grad2 { f2 cumulus, stratocumulus, stratus; };
 // CC:193-198.  REMAP_C(h, 0, c, 0, 1) = h/c (+0, the identity on a non-negative quotient); REMAP_C(h, a, b, 1, 0) = q*(-1) + 1 = 1 - q
-PF Grad2 pLayerGradients(f2 h) {
-    h = pclamp(h, 0.0f, 1.0f);
-    f2 up02 = PDIVC(h, 0.2f - 0.0f), up01 = PDIVC(h, 0.1f - 0.0f);
+PF Grad2 pLayerGradients(f2 h) {                      // h comes clamped from prelativeHeight (layerGradients)
+    f2 up02 = PDIVC(h, 0.2f - 0.0f), up01 = pmul(S2(2.0f), up02);                     // h / 0.1f = 2 * (h / 0.2f), exactly (layerGradients)
     Grad2 g;
     g.cumulus = pmax0(pmul(up02, psub(S2(1.0f), PDIVC(padd(h, S2(-0.7f)), 0.9f - 0.7f))));
-    g.stratocumulus = pmax0(pmul(up02, psub(S2(1.0f), PDIVC(padd(h, S2(-0.2f)), 0.7f - 0.2f))));
+    g.stratocumulus = pmax0(pmul(up02, psub(S2(1.0f), pmul(S2(2.0f), padd(h, S2(-0.2f))))));   // (h - 0.2f) / 0.5f = 2 * (h - 0.2f)
     g.stratus = pmax0(pmul(up01, psub(S2(1.0f), PDIVC(padd(h, S2(-0.2f)), 0.3f - 0.2f))));
     return g;
 }

@@ -70,6 +70,7 @@ struct MarchParams {
     // numbered tile-major (slot = tile * 32 + lane-in-tile, tiles_x tiles per tile row, tile rows in block_row_order)
     unsigned *queue;
     unsigned n_slots, tiles_x;
+    int launch_block_rows;       // host side: entries of block_row_order this launch runs (0 = all of them); sizes grid.y of K1 / K1s / K1x2
 };
 
 struct ReprojectParams {
