@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--variants", default="static,tile,group")
     ap.add_argument("--shard", default="0/1")
+    ap.add_argument("--snake", action="store_true", help="boustrophedon row-cyclic partition (MM_ROWS_SNAKE)")
+    ap.add_argument("--row-block", type=int, default=8)
     ap.add_argument("--all-ranks", action="store_true", help="time every rank's share in turn and print max / mean")
     a = ap.parse_args()
     import torch
@@ -61,7 +63,7 @@ def main():
                 flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                cs.dispatch(mm.MM_FULL, r, n, 8 if n > 1 else 1, stream=stream.cuda_stream)
+                cs.dispatch(mm.MM_FULL | (mm.MM_ROWS_SNAKE if a.snake else 0), r, n, a.row_block if n > 1 else 1, stream=stream.cuda_stream)
                 e1.record(stream)
                 torch.cuda.synchronize()
                 if i >= 2:
