@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--shard", default="0/1")
     ap.add_argument("--snake", action="store_true", help="boustrophedon row-cyclic partition (MM_ROWS_SNAKE)")
     ap.add_argument("--row-block", type=int, default=8)
+    ap.add_argument("--phase16", action="store_true", help="time one MM_PHASE16 dispatch (1/16 of the pixels, phase 5) instead of MM_FULL")
     ap.add_argument("--all-ranks", action="store_true", help="time every rank's share in turn and print max / mean")
     a = ap.parse_args()
     import torch
@@ -39,7 +40,11 @@ def main():
     cs.setFilterMode({"exact": mm.MM_FILTER_EXACT, "hw": mm.MM_FILTER_HW, "hybrid": mm.MM_FILTER_HYBRID}[a.filter])
     if hasattr(cs, "setArithmetic"):
         cs.setArithmetic({"ieee": 0, "fma": 1}[a.arith])
-    cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sc["sun"])
+    sun = sc["sun"].copy()
+    if a.phase16:
+        sun[11] = 5.0                                                    # sun.color.a carries the pixel phase (CC:292)
+    cs.updateUniformBuffers(sc["cam"], None, sc["sky"], sun)
+    mode = mm.MM_PHASE16 if a.phase16 else mm.MM_FULL
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -63,7 +68,7 @@ def main():
                 flush.fill_(1)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                cs.dispatch(mm.MM_FULL | (mm.MM_ROWS_SNAKE if a.snake else 0), r, n, a.row_block if n > 1 else 1, stream=stream.cuda_stream)
+                cs.dispatch(mode | (mm.MM_ROWS_SNAKE if a.snake else 0), r, n, a.row_block if n > 1 else 1, stream=stream.cuda_stream)
                 e1.record(stream)
                 torch.cuda.synchronize()
                 if i >= 2:
