@@ -671,12 +671,12 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     // on several GPUs).  Scheduling only: every variant produces the same bits.
     int lanes = ctx->lanes_per_ray;
     if (lanes == 0) {
-        // measured (tools/shard_probe3.py, tools/variant_bench.sh): one lane per ray wins from ~3 waves up (4 for the sparser,
-        // less coherent rays of a phase dispatch); two lanes win down to under one wave (1080p phase dispatch: 0.45 -> 0.28 ms,
-        // 1/8 of a 1080p frame: 0.43 -> 0.33 ms); four and eight only pay for launches far below one wave
+        // measured (tools/ab_bench.py --phase16 / --shard, profiles/r02_scheduler_ab.txt): one lane per ray wins from ~3 waves up (4
+        // for the sparser, less coherent rays of a phase dispatch); two lanes down to ~1.2 waves (1/8 of a 1080p frame: 0.38 -> 0.30 ms);
+        // four down to ~0.45 (1080p phase dispatch, 0.86 wave: 0.45 -> 0.22 ms); eight below that (720p phase dispatch: 0.47 -> 0.15 ms)
         double waves = (double)p.grid_w * (double)p.owned_rows / ((double)ctx->sm_count * 1024.0);
         double full = (mode == MM_PHASE16) ? 4.0 : MM_SPLIT_WAVES;
-        lanes = waves >= full ? 1 : waves >= 0.75 ? 2 : waves >= 0.3 ? 4 : 8;
+        lanes = waves >= full ? 1 : waves >= 1.2 ? 2 : waves >= 0.45 ? 4 : 8;
     }
     // the ray-split kernels (K1s) exist for power-of-two march textures only (wrap by mask); the texture unit wraps any extent
     bool pow2 = true;

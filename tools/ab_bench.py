@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--shard", default="0/1")
     ap.add_argument("--snake", action="store_true", help="boustrophedon row-cyclic partition (MM_ROWS_SNAKE)")
     ap.add_argument("--row-block", type=int, default=8)
+    ap.add_argument("--size", default="", help="WxH override of the config's extent")
     ap.add_argument("--phase16", action="store_true", help="time one MM_PHASE16 dispatch (1/16 of the pixels, phase 5) instead of MM_FULL")
     ap.add_argument("--all-ranks", action="store_true", help="time every rank's share in turn and print max / mean")
     a = ap.parse_args()
@@ -33,7 +34,8 @@ def main():
     import _pkg
     import scenes
     mm = _pkg.load_package()
-    sc = scenes.make_scene(mm, a.config, scenes.load_assets())
+    wh = {"W": int(a.size.split("x")[0]), "H": int(a.size.split("x")[1])} if a.size else {}
+    sc = scenes.make_scene(mm, a.config, scenes.load_assets(), **wh)
     W, H = sc["W"], sc["H"]
     cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"], lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
     cs.allocOutput()
