@@ -714,13 +714,20 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     // pixels.  When the bound image is a PEER's (ranks != 0 of a sharded frame) the copy engine must not read it -- that would go through the
     // peer's engine and PCIe link -- so those rows are stored to the peer image and to a local staging image, and copied from there.
     static const char *split_env = getenv("MM_E2E_SPLIT");         // diagnostics: "0" keeps every pixel on the kernel-store path
-    if (p.mirror && p.out && mode == MM_FULL && !persistent && nfree > 0 && !(split_env && split_env[0] == '0')) {
+    const char *rest_env = getenv("MM_E2E_REST");                  // diagnostics: "fused" | "copy" | "copy2" overrides the choice below
+    // The rest of the frame: stores fused into the kernel (one launch, nothing after it; the default).  The alternatives -- the copy
+    // engine again, behind one launch ("copy") or behind two launches of which the second overlaps the first one's copies ("copy2") --
+    // are kept for platforms whose mapped stores are slower; on this one they lose at every shard size measured
+    // (4K on 4 GPUs: 1.60 ms fused, 2.30 copy, 2.01 copy2; profiles/r02_e2e_rest_modes.txt).
+    int rest_mode = 0;
+    if (rest_env) rest_mode = rest_env[0] == 'f' ? 0 : (rest_env[4] == '2' ? 2 : 1);
+    if (p.mirror && p.out && mode == MM_FULL && !persistent && (nfree > 0 || rest_mode != 0) && !(split_env && split_env[0] == '0')) {
         auto launch = ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march;
-        static thread_local MarchParams head;
-        head = p;
-        head.mirror = nullptr;
+        float *const host_frame = p.mirror;
+        const size_t host_pitch = p.mirror_pitch;
         const char *copy_src = reinterpret_cast<const char *>(p.out);
         size_t copy_pitch = p.pitch;
+        float *stage = nullptr;                                    // what a launch whose rows go through the copy engine mirrors into
         if (!ctx->out_is_local) {
             const size_t need = (size_t)p.W * p.H * 16;
             if (ctx->e2e_scratch_bytes < need) {
@@ -728,46 +735,62 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
                 CU(cudaMalloc(&ctx->e2e_scratch, need));
                 ctx->e2e_scratch_bytes = need;
             }
-            head.mirror = ctx->e2e_scratch; head.mirror_pitch = (size_t)p.W * 16;
+            stage = ctx->e2e_scratch;
             copy_src = reinterpret_cast<const char *>(ctx->e2e_scratch); copy_pitch = (size_t)p.W * 16;
         }
-        head.launch_block_rows = nfree;                          // the free block rows lead the order when a mirror is bound
-        CU(cudaEventRecord(ctx->ev0, stream));
-        CU(launch(head, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
-        CU(cudaEventRecord(ctx->ev_fork, stream));
-        CU(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        if (nblockrows > nfree) {
-            memmove(p.block_row_order, p.block_row_order + nfree, sizeof(uint16_t) * (size_t)(nblockrows - nfree));
-            p.launch_block_rows = nblockrows - nfree;
-            CU(launch(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream));
-        }
-        // the free rows as runs of consecutive image rows -> one 2D copy per run
-        int run_y = -1, run_n = 0;
-        auto flush = [&]() -> cudaError_t {
-            if (run_n <= 0) return cudaSuccess;
-            cudaError_t e = cudaMemcpy2DAsync(reinterpret_cast<char *>(p.mirror) + (size_t)run_y * p.mirror_pitch, p.mirror_pitch,
-                                              copy_src + (size_t)run_y * copy_pitch, copy_pitch, (size_t)p.W * 16, (size_t)run_n,
-                                              cudaMemcpyDefault, ctx->side);
-            run_n = 0;
-            return e;
-        };
+        static thread_local uint16_t order[sizeof(p.block_row_order) / sizeof(uint16_t)];
+        memcpy(order, p.block_row_order, sizeof(uint16_t) * (size_t)nblockrows);
         static thread_local int rows[4096 * 8];
-        int nrows = 0;
-        for (int i = 0; i < nfree; i++)
-            for (int r = 0; r < block_h; r++) {
-                int j = (int)head.block_row_order[i] * block_h + r;
-                if (j >= p.owned_rows) continue;
-                int k = j / row_block;
-                int py = owned_block(k, row_begin, row_stride, snake) * row_block + (j - k * row_block);
-                if (py < p.H && nrows < 4096 * 8) rows[nrows++] = py;
+        // image rows of block rows order[first .. first+count) as runs of consecutive rows -> one 2D copy per run, on the side stream
+        auto copy_rows = [&](int first, int count) -> cudaError_t {
+            int nrows = 0;
+            for (int i = first; i < first + count; i++)
+                for (int r = 0; r < block_h; r++) {
+                    int j = (int)order[i] * block_h + r;
+                    if (j >= p.owned_rows) continue;
+                    int k = j / row_block;
+                    int py = owned_block(k, row_begin, row_stride, snake) * row_block + (j - k * row_block);
+                    if (py < p.H && nrows < 4096 * 8) rows[nrows++] = py;
+                }
+            std::sort(rows, rows + nrows);
+            int i = 0;
+            while (i < nrows) {
+                int n = 1;
+                while (i + n < nrows && rows[i + n] == rows[i] + n) n++;
+                cudaError_t e = cudaMemcpy2DAsync(reinterpret_cast<char *>(host_frame) + (size_t)rows[i] * host_pitch, host_pitch,
+                                                  copy_src + (size_t)rows[i] * copy_pitch, copy_pitch, (size_t)p.W * 16, (size_t)n,
+                                                  cudaMemcpyDefault, ctx->side);
+                if (e != cudaSuccess) return e;
+                i += n;
             }
-        std::sort(rows, rows + nrows);
-        for (int i = 0; i < nrows; i++) {
-            if (run_n > 0 && rows[i] == run_y + run_n) { run_n++; continue; }
-            CU(flush());
-            run_y = rows[i]; run_n = 1;
+            return cudaSuccess;
+        };
+        // one launch of block rows order[first .. first+count); through_copy_engine: the launch does not touch host memory and its rows
+        // are queued on the side stream behind it
+        auto chunk = [&](int first, int count, bool through_copy_engine) -> cudaError_t {
+            if (count <= 0) return cudaSuccess;
+            memcpy(p.block_row_order, order + first, sizeof(uint16_t) * (size_t)count);
+            p.launch_block_rows = count;
+            p.mirror = through_copy_engine ? stage : host_frame;
+            p.mirror_pitch = through_copy_engine ? (size_t)p.W * 16 : host_pitch;
+            cudaError_t e = launch(p, ctx->filter, lanes, persistent_blocks, ctx->refill, stream);
+            if (e != cudaSuccess || !through_copy_engine) return e;
+            if ((e = cudaEventRecord(ctx->ev_fork, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0)) != cudaSuccess) return e;
+            return copy_rows(first, count);
+        };
+        CU(cudaEventRecord(ctx->ev0, stream));
+        CU(chunk(0, nfree, true));                                 // the free block rows lead the order when a mirror is bound
+        const int nrest = nblockrows - nfree;
+        if (rest_mode == 0) {
+            CU(chunk(nfree, nrest, false));
+        } else if (rest_mode == 1 || nrest < 8) {
+            CU(chunk(nfree, nrest, true));
+        } else {
+            const int first_half = (nrest * 5) / 8;
+            CU(chunk(nfree, first_half, true));
+            CU(chunk(nfree + first_half, nrest - first_half, true));
         }
-        CU(flush());
         CU(cudaEventRecord(ctx->ev_join, ctx->side));
         CU(cudaStreamWaitEvent(stream, ctx->ev_join, 0));
         CU(cudaEventRecord(ctx->ev1, stream));

@@ -423,6 +423,43 @@ def test_render_to_host_pinned_and_pageable_agree(mm, assets):
     assert np.array_equal(pinned.view(np.uint32), device.view(np.uint32))
 
 
+@pytest.mark.parametrize("rest", ["fused", "copy", "copy2", None])
+@pytest.mark.parametrize("pitch_deg", [0.0, 50.0])
+def test_host_mirror_paths_deliver_the_same_frame(mm, assets, rest, pitch_deg, monkeypatch):
+    """The mirrored dispatch has three ways to get a row into host memory (stores fused into the kernel, the copy engine behind
+    one launch, the copy engine behind two launches; mm_dispatch picks by the kind of dispatch, MM_E2E_REST forces one).  Every one
+    must deliver the device image bit for bit, for whole frames and for shares of a sharded frame, with and without rows below
+    the horizon (a camera pitched up has none)."""
+    import torch
+    if rest is None:
+        monkeypatch.delenv("MM_E2E_REST", raising=False)
+    else:
+        monkeypatch.setenv("MM_E2E_REST", rest)
+    W, H = 211, 173
+    sc = scenes.make_scene(mm, "C1", assets, W=W, H=H, pitch=np.radians(-20.0 + pitch_deg))
+    cam = sc["cam"]
+    cs = mm.ComputeShader(0, (W, H), placement=sc["textures"]["placement"], curl=sc["textures"]["curl"],
+                          lowRes=sc["textures"]["lowres"], hiRes=sc["textures"]["hires"])
+    cs.allocOutput()
+    cs.updateUniformBuffers(cam, None, sc["sky"], sc["sun"])
+    pinned = torch.full((H, W, 4), -7.0, dtype=torch.float32).pin_memory()
+    cs.bindHostMirror(pinned.numpy())
+    cs.dispatch(mm.MM_FULL)
+    cs.synchronize()
+    whole = cs.readOutput()
+    assert np.array_equal(pinned.numpy().view(np.uint32), whole.view(np.uint32))
+    for begin, stride in ((1, 3), (2, 4), (7, 8)):
+        pinned.fill_(-7.0)
+        cs.dispatch(mm.MM_FULL, begin, stride, 8)
+        cs.synchronize()
+        rows = mm.multigpu.owned_rows(H, begin, stride, 8)
+        other = np.setdiff1d(np.arange(H), rows)
+        got = pinned.numpy()
+        assert (got[other] == -7.0).all()
+        assert np.array_equal(got[rows].view(np.uint32), whole[rows].view(np.uint32)), (rest, begin, stride)
+    cs.close()
+
+
 def test_bound_host_mirror_receives_every_dispatch(mm, assets):
     """mm_bind_host_mirror: every dispatch also stores its pixels into a page-locked host frame (what each rank of a sharded
     frame does with the shared host frame); the host frame equals the device image bit for bit, for full and partial dispatches."""
