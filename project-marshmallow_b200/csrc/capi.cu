@@ -720,7 +720,7 @@ int mm_dispatch(mm_ctx *ctx, int mode, int row_begin, int row_stride, int row_bl
     // are kept for platforms whose mapped stores are slower; on this one they lose at every shard size measured
     // (4K on 4 GPUs: 1.60 ms fused, 2.30 copy, 2.01 copy2; profiles/r02_e2e_rest_modes.txt).
     int rest_mode = 0;
-    if (rest_env) rest_mode = rest_env[0] == 'f' ? 0 : (rest_env[4] == '2' ? 2 : 1);
+    if (rest_env) rest_mode = !strcmp(rest_env, "copy2") ? 2 : !strcmp(rest_env, "copy") ? 1 : 0;
     if (p.mirror && p.out && mode == MM_FULL && !persistent && (nfree > 0 || rest_mode != 0) && !(split_env && split_env[0] == '0')) {
         auto launch = ctx->arith == MM_ARITH_FMA ? launch_cloud_march_fma : launch_cloud_march;
         float *const host_frame = p.mirror;
