@@ -461,6 +461,28 @@ static float *g_trace = NULL; static size_t g_trace_cap = 0, g_trace_n = 0;
 void om_debug_trace(float *buf, size_t capacity_records) { g_trace = buf; g_trace_cap = capacity_records; g_trace_n = 0; }
 size_t om_debug_trace_count(void) { return g_trace_n; }
 
+/* Diagnostics (tools/pow_filter_bound.py): could a march trip have skipped the deterministic pow of CC:245?  With a cheap estimate c~ of
+ * coverage = h^k, relative error <= POWF_DELTA, the result of CC:247-250 is decided without the exact value when
+ *   class 1: fbm < c~(1-d)            -> coverage > fbm, the erosion remap clamps to 0 and the result is min(gate density, 1);
+ *   class 2: fbm > c~(1+d) by a margin and density(1-c) - (fbm-c) < -margin at both ends of c~(1 -+ d) (linear in c) -> the result is +0;
+ *   class 3: neither (the exact pow is needed);  class 0: k == 1 (coverage <= 0.7), no pow at all.
+ * The prediction is checked against the exact result bit for bit; mismatches are counted in om_powclass_mismatches. */
+unsigned long long om_powclass_mismatches = 0;
+#define POWF_DELTA 1e-4f
+#define POWF_MARGIN 1e-5f
+static int pow_filter_class(float h, float cov, float gateDensity, float fbm, float exact) {
+    if (!(cov > 0.7f)) return 0;
+    float k = clampf(remapf(cov, 0.7f, 0.8f, 1.0f, 0.8f), 0.8f, 1.0f);
+    if (k == 1.0f) return 0;
+    float c = exp2f(k * log2f(h)), lo = c * (1.0f - POWF_DELTA), hi = c * (1.0f + POWF_DELTA);
+    int cls = 3; float predicted = exact;
+    const float a = gateDensity - fbm, b = 1.0f - gateDensity;
+    if (fbm < lo) { cls = 1; predicted = ominf(gateDensity, 1.0f); }
+    else if (fbm - hi > POWF_MARGIN && fmaf(hi, b, a) < -POWF_MARGIN && fmaf(lo, b, a) < -POWF_MARGIN) { cls = 2; predicted = 0.0f; }
+    if (memcmp(&predicted, &exact, 4) != 0) { _Pragma("omp atomic") om_powclass_mismatches++; }
+    return cls;
+}
+
 /* CC:231-253 (Q2: heightBiasCoverage called with swapped arguments) */
 static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     const struct om_scene *s = cx->s;
@@ -489,8 +511,11 @@ static float cloudTest(const ctx_t *cx, v3 pos, float relativeHeight) {
     int k_is_one = !(ci[0] > 0.7f);
 
     float erosion = ((0.625f * dn[1]) + (0.25f * dn[2])) + (0.125f * dn[3]);
+    const float gateDensity = density, fbm = erosion;
     erosion = remapClampedf(erosion, coverage, 1.0f, 0.0f, 1.0f);
     density = remapClampedf(density, erosion, 1.0f, 0.0f, 1.0f);
+    if (cx->cnt->powclass && !cx->cnt->in_light && cx->cnt->trips - 1 < 256)
+        cx->cnt->powclass[cx->cnt->trips - 1] = (uint8_t)pow_filter_class(relativeHeight, ominf(0.85f, ci[0]), gateDensity, fbm, density);
     if (trace) trace[6] = density;
     if (density > 0.0f) STAT(4); else STAT(3);
     if (k_is_one) STAT(5);
@@ -718,6 +743,7 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
             cnt->lit++;
             if (cnt->litmask && cnt->trips - 1 < 256) cnt->litmask[(cnt->trips - 1) >> 5] |= 1u << ((cnt->trips - 1) & 31);
             float densityAlongLight = 0.0f;
+            cnt->in_light = 1;
             for (int i = 0; i < 6; i++) {                                         /* CC:441-453 */
                 v3 lsPos = add3(currentPos, scale3(3.0f * stepSize, samples[i]));
                 v3 lsProj = getProjectedShellPoint(lsPos, earthCenter);
@@ -730,6 +756,7 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
                     densityAlongLight += lsDensity;
                 }
             }
+            cnt->in_light = 0;
             float beersLaw = expf(-densityAlongLight);                            /* CC:456-466 (Q10) */
             float beersModulated = omaxf(beersLaw, 0.7f * expf(-0.25f * densityAlongLight));
             beersLaw = mixf(beersLaw, beersModulated, ((-cosTheta) * 0.5f) + 0.5f);
@@ -783,6 +810,8 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
  */
 static uint32_t *g_litmask = NULL;   /* diagnostics: 8 x uint32 per pixel, set with om_set_litmask_buffer */
 void om_set_litmask_buffer(uint32_t *buf) { g_litmask = buf; }
+static uint8_t *g_powclass = NULL;   /* diagnostics: 256 bytes per pixel (zeroed by the caller), see pow_filter_class */
+void om_set_powclass_buffer(uint8_t *buf) { g_powclass = buf; }
 
 int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_stride, int row_block,
              float *out_rgba32f, uint32_t *counters, int nthreads) {
@@ -805,7 +834,7 @@ int om_march(const om_scene *s, int mode, int W, int H, int row_begin, int row_s
         if (mode == OM_PHASE16 && (y % 4) != oy) continue;
         for (int x = 0; x < W; x++) {
             if (mode == OM_PHASE16 && (x % 4) != ox) continue;
-            px_counters c = {0, 0, 0, 0, g_litmask ? g_litmask + 8 * ((size_t)y * W + x) : NULL};
+            px_counters c = {0, 0, 0, 0, g_litmask ? g_litmask + 8 * ((size_t)y * W + x) : NULL, g_powclass ? g_powclass + 256 * ((size_t)y * W + x) : NULL, 0};
             float o[4];
             if (s->arith == OM_ARITH_FMA) om__march_pixel_fma(s, x, y, W, H, o, &c);
             else march_pixel(s, x, y, W, H, o, &c);

@@ -22,7 +22,8 @@ struct om_scene {
     int arith;       /* OM_ARITH_*  */
 };
 
-typedef struct { uint32_t trips, n2d, n3d, lit; uint32_t *litmask; /* optional: bit k set = loop iteration k was a lit step (k < 256) */ } px_counters;
+typedef struct { uint32_t trips, n2d, n3d, lit; uint32_t *litmask; /* optional: bit k set = loop iteration k was a lit step (k < 256) */
+                 uint8_t *powclass; int in_light; /* diagnostics of tools/pow_filter_bound.py: class of the march trip's coverage pow, 256 trips per pixel */ } px_counters;
 
 
 /* the software sampler of cloud_march_oracle.c (Texture.cpp:29-52, 315-338 in the three filter definitions) */
