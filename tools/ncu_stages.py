@@ -2,7 +2,7 @@
 """Stage-level profile of the march kernel: join an ncu SASS source page with nvdisasm's INLINE line chains and
 attribute every executed instruction to a stage of the march (where in cloud_march.cu the OUTERMOST non-trivial call site lies).
 
-usage: python tools/ncu_stages.py report.ncu-rep lib.so 'cloud_march_kernelILb1ELb1ELb0ELb1E' [--per-trip]
+usage: python tools/ncu_stages.py report.ncu-rep lib.so|cloud_march.cu.o 'cloud_march_kernelILb1ELb1ELb0ELb1E' [cloud_march.cu of that build]
 
 ncu_lines.py answers "which source line"; helpers such as dot / mad3 / mixg are inlined everywhere, so their lines collect a third of
 the kernel.  Here the chain  `line 49 inlined at line 68 inlined at line 385 inlined at line 763 ...`  is walked from the innermost
@@ -11,7 +11,7 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, lib, kpat = sys.argv[1:4]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = os.path.join(ROOT, "project-marshmallow_b200", "csrc", "cloud_march.cu")
+SRC = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "project-marshmallow_b200", "csrc", "cloud_march.cu")   # the source `lib` was built from
 src_lines = open(SRC).read().splitlines()
 
 
