@@ -70,17 +70,28 @@ class HostBarrier:
     every process has mapped (at least world * 64 bytes, zero-initialised).  wait() publishes this rank's next epoch and spins until
     every rank has published it.  x86 stores are ordered, and the ranks only ever increase their own slot."""
 
-    def __init__(self, buffer, rank, world, offset=0):
+    def __init__(self, buffer, rank, world, offset=0, timeout_s=120.0):
         self.rank = rank
         self._epochs = np.frombuffer(buffer, dtype=np.int64, count=world * 8, offset=offset)[::8]
         self._epoch = 0
+        self._timeout_s = timeout_s
 
     def wait(self):
+        """Raises RuntimeError when a rank has not arrived within `timeout_s` (a peer process died): a sharded frame must fail, not hang."""
+        import time
         self._epoch += 1
         self._epochs[self.rank] = self._epoch
         e = self._epochs
+        spins, deadline = 0, None
         while int(e.min()) < self._epoch:
-            pass
+            spins += 1
+            if (spins & 0xfff) == 0:                  # look at the clock every 4096 polls only: the common wait is microseconds
+                now = time.monotonic()
+                if deadline is None:
+                    deadline = now + self._timeout_s
+                elif now > deadline:
+                    late = [r for r, v in enumerate(e.tolist()) if v < self._epoch]
+                    raise RuntimeError(f"HostBarrier: ranks {late} did not reach epoch {self._epoch} within {self._timeout_s:.0f} s")
 
     def release(self):
         self._epochs = None

@@ -153,3 +153,15 @@ def test_host_barrier_orders_the_ranks(tmp_path):
     for p in ps:
         p.join(timeout=30)
     assert res == [(r, True) for r in range(world)]
+
+
+def test_host_barrier_fails_instead_of_hanging_when_a_rank_is_missing(mm):
+    """A peer process that died must turn into an error on the surviving ranks, not into a spin until the job's time limit."""
+    import time
+    buf = bytearray(4096)
+    b = mm.multigpu.HostBarrier(buf, 0, 2, offset=0, timeout_s=0.2)
+    t0 = time.monotonic()
+    with pytest.raises(RuntimeError, match=r"ranks \[1\] did not reach epoch 1"):
+        b.wait()
+    assert time.monotonic() - t0 < 5.0
+    b.release()
