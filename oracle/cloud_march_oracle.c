@@ -724,6 +724,7 @@ static void march_pixel(const struct om_scene *s, int px, int py, int W, int H, 
         v3 currentPos = add3(cameraPos, scale3(t, rayDirection));
         v3 currentProj = getProjectedShellPoint(currentPos, earthCenter);
         float rHeight = getRelativeHeight(currentPos, currentProj, atmosphereThickness);
+        if (cnt->powclass && cnt->trips - 1 < 256 && rHeight >= 0.901f) cnt->powclass[cnt->trips - 1] |= 0x80;   /* diagnostics: trip above every height gradient */
         v3 windOffset = scale3((timeOffset + (rHeight * 200.0f)),
                                scale3(WIND_STRENGTH, add3(windXYZ, scale3(rHeight, V3(0.1f, 0.05f, 0.0f)))));    /* CC:414 (Q8) */
 

@@ -39,7 +39,8 @@ def main():
     _, cnt = S.march(W, H, row_begin=0, row_stride=a.stride, row_block=4, nthreads=os.cpu_count())
     lib.om_set_powclass_buffer(None)
     mism = C.c_ulonglong.in_dll(lib, "om_powclass_mismatches").value
-    cls = buf[rows]                                           # [owned rows][W][256]
+    top = buf[rows] >> 7                                      # bit 7: the trip's height is above every height gradient (h >= 0.901)
+    cls = buf[rows] & 0x7f                                    # [owned rows][W][256]
     trips = cnt[rows][..., 0]
     nrows = len(rows) // 4 * 4
     cls = cls[:nrows].reshape(nrows // 4, 4, W // 8, 8, 256).transpose(0, 2, 1, 3, 4).reshape(-1, 32, 256)      # [tile][lane][trip]
@@ -58,6 +59,18 @@ def main():
     lanes_now = calls.sum(axis=1)[pay_now].mean()
     print(f"  warp level: {pay_now.sum() / warp_trips:.3f} of warp-trips call the pow today ({lanes_now:.1f} lanes in it on average); "
           f"with the filter {pay_filtered.sum() / warp_trips:.3f} -> {1 - pay_filtered.sum() / max(1, pay_now.sum()):.3f} of the calls avoided")
+    # Second question, same trace: once a ray is above every height gradient (h >= 0.901: cumulus, stratocumulus and stratus are all exactly 0) it stays
+    # there -- the distance from the earth's centre grows along an upward ray -- and every remaining trip is a miss whose only effects are the counters of
+    # CC:468-481 and t += stepSize.  A warp whose live lanes have all been SEEN in that zone on an earlier trip could run those trips without the ~150
+    # instructions of position / height / gradients.  How many warp-trips is that?
+    top = top[:nrows].reshape(nrows // 4, 4, W // 8, 8, 256).transpose(0, 2, 1, 3, 4).reshape(-1, 32, 256)
+    n_idx = np.arange(256)[None, None, :]
+    live = n_idx < trips[:, :, None]                          # lane executes trip n
+    seen_before = (np.cumsum(top, axis=2) - top) > 0          # flagged on an earlier trip
+    assert not (seen_before & live & (top == 0)).any(), "a ray left the top zone again"
+    skippable = live.any(axis=1) & ~(live & ~seen_before).any(axis=1)
+    print(f"  top zone (h >= 0.901): {(top.astype(bool) & live).sum() / lane_trips:.3f} of lane-trips lie in it; warp-trips in which EVERY live lane was already seen there "
+          f"(skippable without computing a height): {skippable.sum() / warp_trips:.3f}")
     assert mism == 0, "the filter mispredicted an outcome"
 
 
