@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Stage-level profile of the march kernel: join an ncu SASS source page with nvdisasm's INLINE line chains and
-attribute every executed instruction to a stage of the march (where in cloud_march.cu the OUTERMOST non-trivial call site lies).
+attribute every executed instruction to a stage of the march (where in cloud_march.cu / cloud_march_ray.inl the call site lies).
 
-usage: python tools/ncu_stages.py report.ncu-rep lib.so|cloud_march.cu.o 'cloud_march_kernelILb1ELb1ELb0ELb1E' [cloud_march.cu of that build]
+usage: python tools/ncu_stages.py report.ncu-rep lib.so|cloud_march.cu.o 'cloud_march_kernelILb1ELb1ELb0ELb1E' [csrc directory of that build]
 
 ncu_lines.py answers "which source line"; helpers such as dot / mad3 / mixg are inlined everywhere, so their lines collect a third of
 the kernel.  Here the chain  `line 49 inlined at line 68 inlined at line 385 inlined at line 763 ...`  is walked from the innermost
@@ -11,55 +11,69 @@ import collections, csv, io, os, re, subprocess, sys, tempfile
 
 rep, lib, kpat = sys.argv[1:4]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SRC = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "project-marshmallow_b200", "csrc", "cloud_march.cu")   # the source `lib` was built from
-src_lines = open(SRC).read().splitlines()
+CSRC = sys.argv[4] if len(sys.argv) > 4 else os.path.join(ROOT, "project-marshmallow_b200", "csrc")   # directory of the sources `lib` was built from
+SOURCES = {f: open(os.path.join(CSRC, f)).read().splitlines() for f in ("cloud_march.cu", "cloud_march_ray.inl") if os.path.exists(os.path.join(CSRC, f))}
 
 
-def find(pat, start=0):
-    for i in range(start, len(src_lines)):
-        if re.search(pat, src_lines[i]):
-            return i + 1
-    raise SystemExit("pattern not found in cloud_march.cu: " + pat)
+def find(pat, start=None):
+    """(file, line) of the first line matching pat; start = (file, line) restricts the search to that file from that line on"""
+    for f, lines in SOURCES.items():
+        if start and f != start[0]:
+            continue
+        for i in range(start[1] - 1 if start else 0, len(lines)):
+            if re.search(pat, lines[i]):
+                return f, i + 1
+    raise SystemExit("pattern not found in the march sources: " + pat)
 
 
 def body(pat):
-    """(first, last) line of the function whose signature matches pat (brace matching from its first '{')"""
-    a = find(pat)
-    depth, seen = 0, False
-    for i in range(a - 1, len(src_lines)):
-        for ch in src_lines[i]:
+    """(file, first, last) line of the function whose signature matches pat (brace matching from its first '{')"""
+    f, a = find(pat)
+    lines, depth, seen = SOURCES[f], 0, False
+    for i in range(a - 1, len(lines)):
+        for ch in lines[i]:
             if ch == "{": depth += 1; seen = True
             elif ch == "}": depth -= 1
         if seen and depth == 0:
-            return a, i + 1
+            return f, a, i + 1
     raise SystemExit("unbalanced braces after " + pat)
+
+
+def span(first, last):
+    assert first[0] == last[0]
+    return first[0], first[1], last[1]
+
+
+def before(pos):
+    return pos[0], pos[1] - 1
 
 
 # stages, innermost-first priority: the first frame (walking outwards) that lies in one of these ranges names the instruction
 trip = body(r"void warp_trip\(")
 ct = body(r"float cloudTest\(")
-t_call_test = find(r"density = cloudTest<MARCH_HW", trip[0])
-t_ballot = find(r"litMask = __ballot_sync", trip[0])
+trip0, trip1, ct0, ct1 = (trip[0], trip[1]), (trip[0], trip[2]), (ct[0], ct[1]), (ct[0], ct[2])
+t_call_test = find(r"density = cloudTest<MARCH_HW", trip0)
+t_ballot = find(r"litMask = __ballot_sync", trip0)
 t_tail = find(r"if \(r\.alive\) \{", t_ballot)
-c_fetch = find(r"Fetch3<HW, P2> dn\(P\.tex\[TEX_LOWRES\]", ct[0])
-c_blend = find(r"float layerDensity = blendLayers", ct[0])
-c_cov = find(r"float k = clampg\(REMAP_C\(gmin", ct[0])
-c_ero = find(r"float2 nzw = dn", ct[0])
+c_fetch = find(r"Fetch3<HW, P2> dn\(P\.tex\[TEX_LOWRES\]", ct0)
+c_blend = find(r"float layerDensity = blendLayers", ct0)
+c_cov = find(r"float k = clampg\(REMAP_C\(gmin", ct0)
+c_ero = find(r"float2 nzw = dn", ct0)
 STAGES = [
     ("light sample, relaxed arithmetic (lightSampleFast)", body(r"float lightSampleFast\(")),
     ("light samples: dealing (item, sample) pairs through shared memory", body(r"float warpSharedLightSamples\(")),
     ("lit term: Beer / in-scatter / phase (litTerm)", body(r"float litTerm\(")),
     ("det_powf (binary64 pow of the coverage bias)", body(r"float det_powf\(")),
     ("cloudHiRes (curl + hi-res fetch, erosion, remap)", body(r"float cloudHiRes\(")),
-    ("cloudTest: height gradients + all-zero early out", (ct[0], c_fetch - 1)),
-    ("cloudTest: low-res + placement fetch (shell projection, coordinates)", (c_fetch, c_blend - 1)),
-    ("cloudTest: layer blend, density gate", (c_blend, c_cov - 1)),
-    ("cloudTest: coverage bias (remap, pow call)", (c_cov, c_ero - 1)),
-    ("cloudTest: erosion, exact early-out, two remaps", (c_ero, ct[1])),
-    ("trip: position, shell projection, height, wind offset", (trip[0], t_call_test)),
-    ("trip: hit / miss state machine (CC:426-437, 468-474)", (t_call_test + 1, t_ballot - 1)),
-    ("trip: lit-lane ballot, transmittance update", (t_ballot, t_tail - 1)),
-    ("trip: termination tests, t += step (CC:476-482, 408)", (t_tail, trip[1])),
+    ("cloudTest: height gradients + all-zero early out", span(ct0, before(c_fetch))),
+    ("cloudTest: low-res + placement fetch (shell projection, coordinates)", span(c_fetch, before(c_blend))),
+    ("cloudTest: layer blend, density gate", span(c_blend, before(c_cov))),
+    ("cloudTest: coverage bias (remap, pow call)", span(c_cov, before(c_ero))),
+    ("cloudTest: erosion, exact early-out, two remaps", span(c_ero, ct1)),
+    ("trip: position, shell projection, height, wind offset", span(trip0, t_call_test)),
+    ("trip: hit / miss state machine (CC:426-437, 468-474)", span((t_call_test[0], t_call_test[1] + 1), before(t_ballot))),
+    ("trip: lit-lane ballot, transmittance update", span(t_ballot, before(t_tail))),
+    ("trip: termination tests, t += step (CC:476-482, 408)", span(t_tail, trip1)),
     ("ray set-up: sky colour (atmosphereColorPhysical)", body(r"v3 atmosphereColorPhysical\(")),
     ("ray set-up: shell intersections (raySphereT)", body(r"float raySphereT\(")),
     ("ray set-up: night background", body(r"v3 nightBackground\(")),
@@ -73,10 +87,10 @@ STAGES = [
 
 def stage_of(chain):
     for f, line in chain:                                    # innermost frame first
-        if f != "cloud_march.cu":
+        if f not in SOURCES:
             continue
-        for name, (a, b) in STAGES:
-            if a <= line <= b:
+        for name, (sf, a, b) in STAGES:
+            if sf == f and a <= line <= b:
                 return name
     return "other (libm slow paths, CUDA headers)"
 
