@@ -121,3 +121,19 @@ def test_pow_filter_changes_no_bit(host_march, mm, assets, name, W, H):
             b, cb = _host_frame(plain, sc, W, H, filt, counters, S, om_filter)
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ca, cb), (filt, counters)
     S.close()
+
+
+@pytest.mark.parametrize("name", ["C3", "C2"])
+def test_march_source_on_a_larger_frame(host_march, mm, assets, name):
+    """83 k rays per scene and sampler: the rarer paths (rays grazing the horizon with 250 trips, the 10-miss rule, saturated accumulations)"""
+    W, H = 384, 216
+    sc = scenes.make_scene(mm, name, assets, W=W, H=H)
+    for filt, om_filter in ((FILTER_HW, ob.OM_FILTER_TEXUNIT), (FILTER_EXACT, ob.OM_FILTER_FP32)):
+        S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=om_filter)
+        want, want_cnt = S.march(W, H)
+        got, cnt = _host_frame(host_march[False], sc, W, H, filt, True, S, om_filter)
+        assert want_cnt[..., 0].max() >= 200                 # the long rays are in the frame
+        assert np.array_equal(cnt, want_cnt)
+        assert np.array_equal(got[..., 3].view(np.uint32), want[..., 3].view(np.uint32))
+        assert ob.parity_report(want, got)["pass"]
+        S.close()
