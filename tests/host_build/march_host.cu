@@ -207,4 +207,50 @@ int hm_march(const float *camera160, const float *sun116, const float *sky52, co
 
 float hm_det_powf(float x, float y) { return mm::det_powf(x, y); }
 
+// K7 (cloud_shadow_kernel): accumDensity and texture() counts for n world positions.  filter: 0 FILTER_EXACT, 1 FILTER_HW.  Not built under MM_FMA (the product
+// has the pass once, in the uncontracted build).
+int hm_cloud_shadow(const float *camera160, const float *sun116, const float *sky52, const uint8_t *placement, int pw, int ph, const uint8_t *lowres, int ln,
+                    int filter, const float *positions_xyz, int n, void *sampler, void *user, float *out_density, uint32_t *out_fetches) {
+    using namespace mm;
+#if MM_FMA
+    return -3;
+#else
+    if (!camera160 || !sun116 || !sky52 || !placement || !lowres || !positions_xyz || !out_density || n < 0) return -1;
+    if (filter == FILTER_HW && !sampler) return -2;
+    mm_host::g_sampler = (mm_host::sampler_fn)sampler;
+    mm_host::g_user = user;
+    ShadowParams P;
+    memset(&P, 0, sizeof P);
+    memcpy(P.cam, camera160, 160); memcpy(P.sun, sun116, 116); memcpy(P.sky, sky52, 52);
+    {   // capi.cu, mm_cloud_shadow: L = normalize((camera.view * vec4(sun.directionBasis[1].xyz, 0)).xyz); if (L.y < -0.05) L *= -1  (model.frag:216-217)
+        const float *c = P.cam, *d = P.sun + 16;
+        float l[3];
+        for (int i = 0; i < 3; i++) {
+            volatile float p0 = c[0 + i] * d[0], p1 = c[4 + i] * d[1], p2 = c[8 + i] * d[2], p3 = c[12 + i] * 0.0f;
+            volatile float sum = p0 + p1;
+            sum = sum + p2;
+            sum = sum + p3;
+            l[i] = sum;
+        }
+        volatile float xx = l[0] * l[0], yy = l[1] * l[1], zz = l[2] * l[2];
+        volatile float dd = xx + yy;
+        dd = dd + zz;
+        volatile float inv = 1.0f / sqrtf(dd);
+        for (int i = 0; i < 3; i++) { volatile float v = l[i] * inv; P.L[i] = v; }
+        if (P.L[1] < -0.05f) for (int i = 0; i < 3; i++) { volatile float v = -1.0f * P.L[i]; P.L[i] = v; }
+    }
+    std::vector<float4> pp = pack_pairs(placement, pw, ph, 1, true), lp = pack_pairs(lowres, ln, ln, ln, false);
+    P.placement = TexDev{pp.data(), (cudaTextureObject_t)(TEX_PLACEMENT + 1), pw, ph, 1, (float)pw, (float)ph, 1.0f, is_pow2(pw) && is_pow2(ph)};
+    P.lowres = TexDev{lp.data(), (cudaTextureObject_t)(TEX_LOWRES + 1), ln, ln, ln, (float)ln, (float)ln, (float)ln, is_pow2(ln)};
+    P.pos = positions_xyz; P.n = n;
+    const bool p2 = P.placement.pow2 && P.lowres.pow2;
+    for (int i = 0; i < n; i++) {
+        uint32_t nf;
+        out_density[i] = filter == FILTER_HW ? shadowPoint<true, true>(P, i, nf) : p2 ? shadowPoint<false, true>(P, i, nf) : shadowPoint<false, false>(P, i, nf);
+        if (out_fetches) out_fetches[i] = nf;
+    }
+    return 0;
+#endif
+}
+
 }  // extern "C"

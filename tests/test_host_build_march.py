@@ -33,6 +33,7 @@ def _build(fma, extra=(), tag=""):
     l = C.CDLL(lib)
     l.hm_march.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p] * 4
     l.hm_det_powf.restype, l.hm_det_powf.argtypes = C.c_float, [C.c_float, C.c_float]
+    l.hm_cloud_shadow.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int] + [C.c_void_p] * 4
     assert l.hm_arith() == int(fma)
     return l
 
@@ -136,4 +137,25 @@ def test_march_source_on_a_larger_frame(host_march, mm, assets, name):
         assert np.array_equal(cnt, want_cnt)
         assert np.array_equal(got[..., 3].view(np.uint32), want[..., 3].view(np.uint32))
         assert ob.parity_report(want, got)["pass"]
+        S.close()
+
+
+@pytest.mark.parametrize("name,over", [("C1", {}), ("C3", {}), ("C1", {"wind": (1.0, 0.05, 1.0), "time": 37.5}), ("C5", {})])
+def test_cloud_shadow_source_is_bit_exact(host_march, mm, assets, name, over):
+    """K7 (model.frag:240-283): the per-point source against om_cloud_shadow, densities and texture() counts bit for bit, both sampler definitions"""
+    sc = scenes.make_scene(mm, name, assets, W=64, H=36, **over)
+    rng = np.random.default_rng(11)
+    pos = (rng.uniform(-1.0, 1.0, (20000, 3)) * np.array([30000.0, 400.0, 30000.0])).astype(np.float32)
+    cam, sun, sky = (np.ascontiguousarray(x, np.float32) for x in (sc["cam"], sc["sun"], sc["sky"]))
+    pl, lo = np.ascontiguousarray(sc["textures"]["placement"], np.uint8), np.ascontiguousarray(sc["textures"]["lowres"], np.uint8)
+    for filt, om_filter in ((FILTER_EXACT, ob.OM_FILTER_FP32), (FILTER_HW, ob.OM_FILTER_TEXUNIT)):
+        S = ob.Scene(sc["textures"], sc["cam"], sc["sun"], sc["sky"], filter_mode=om_filter)
+        want, want_nf = S.cloud_shadow(pos, want_fetches=True)
+        got, nf = np.empty(len(pos), np.float32), np.empty(len(pos), np.uint32)
+        ctx = _SamplerCtx(S.s, om_filter)
+        rc = host_march[False].hm_cloud_shadow(ob._p(cam), ob._p(sun), ob._p(sky), ob._p(pl), pl.shape[1], pl.shape[0], ob._p(lo), lo.shape[0], filt, ob._p(pos), len(pos),
+                                               C.cast(ob.lib().om_sample_callback, C.c_void_p), C.cast(C.byref(ctx), C.c_void_p), ob._p(got), ob._p(nf))
+        assert rc == 0
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)) and np.array_equal(nf, want_nf)
+        assert (want > 0).mean() > 0.02 or name == "C5"      # the positions do reach cloud
         S.close()
