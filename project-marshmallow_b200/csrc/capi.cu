@@ -21,6 +21,7 @@
 
 #include "../../include/marshmallow.h"
 #include "common.h"
+#include "curl_table.h"
 
 using namespace mm;
 
@@ -264,21 +265,6 @@ static int upload(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h, int
 
 int mm_upload_tex2d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h) { return upload(ctx, slot, rgba8, w, h, 1, false); }
 int mm_upload_tex3d(mm_ctx *ctx, int slot, const uint8_t *rgba8, int w, int h, int d) { return upload(ctx, slot, rgba8, w, h, d, true); }
-
-// Gradient index of every lattice point the curl-noise Perlin can touch (coordinates -1..24, stored at
-// +1), following hashNoise / hashVec (ImageUtils.cpp:25-34) with the host C library's sinf -- see the
-// header of curl_noise.cu for why this one step stays on the host.
-static void build_curl_gradient_table(unsigned char *table) {
-    const float kx = 12.9898f, ky = 78.233f, kz = (float)47.387;
-    for (int z = -1; z < 25; z++)
-        for (int y = -1; y < 25; y++)
-            for (int x = -1; x < 25; x++) {
-                float d = (((float)x * kx) + ((float)y * ky)) + ((float)z * kz);
-                float n = sinf(d) * 43758.5453f;
-                n = n - floorf(n);
-                table[((z + 1) * 26 + (y + 1)) * 26 + (x + 1)] = (unsigned char)(int)floorf(12.f * n);
-            }
-}
 
 int mm_build_curl_noise(mm_ctx *ctx, uint8_t *out_host) {
     if (!ctx) return MM_ERR_ARG;

@@ -1,9 +1,12 @@
-// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
+// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K2 (curl_noise_pixel.h), K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
 // the CPU, so that the CPU test-suite (tests/test_host_build.py) can compare the product's kernel arithmetic with the oracle without a GPU.  The loops below do
 // what the kernels of reproject.cu / post_chain.cu do with the same functions; nothing here is linked into the product library.
+#define MM_HOST_BUILD 1
 #include <cstdint>
 #include <vector>
 
+#include "../../project-marshmallow_b200/csrc/curl_noise_pixel.h"
+#include "../../project-marshmallow_b200/csrc/curl_table.h"
 #include "../../project-marshmallow_b200/csrc/post_chain_pixel.h"
 #include "../../project-marshmallow_b200/csrc/reproject_pixel.h"
 
@@ -88,6 +91,24 @@ int hb_reproject(const float *camera160, const float *camera_prev160, const floa
             float *o = dst + ((size_t)y * W + x) * 4;
             o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
         }
+    return 0;
+}
+
+// launch_curl_noise (curl_noise.cu): 12 FBM probes per texel, curl, global per-channel bounds, normalise + quantise -> 128 x 128 RGBA8
+int hb_curl_noise(uint8_t *dst_rgba8) {
+    const int N = 128 * 128;
+    std::vector<unsigned char> table(26 * 26 * 26);
+    build_curl_gradient_table(table.data());
+    std::vector<float> fbm12((size_t)12 * N), curls((size_t)3 * N);
+    float bounds[6] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+    for (int gid = 0; gid < 12 * N; gid++) fbm12[gid] = curl_pixel::curl_probe(table.data(), gid);
+    for (int pix = 0; pix < N; pix++) curl_pixel::curl_combine(fbm12.data(), curls.data(), pix);
+    for (int pix = 0; pix < N; pix++)                         // curl_bounds_kernel: min / max are order-independent
+        for (int c = 0; c < 3; c++) { float v = curls[3 * pix + c]; bounds[c] = fminf(bounds[c], v); bounds[3 + c] = fmaxf(bounds[3 + c], v); }
+    for (int pix = 0; pix < N; pix++) {
+        uchar4 q = curl_pixel::curl_quantise(curls.data(), bounds, pix);
+        dst_rgba8[4 * pix] = q.x; dst_rgba8[4 * pix + 1] = q.y; dst_rgba8[4 * pix + 2] = q.z; dst_rgba8[4 * pix + 3] = q.w;
+    }
     return 0;
 }
 
