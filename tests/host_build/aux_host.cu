@@ -1,4 +1,4 @@
-// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K2 (curl_noise_pixel.h), K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
+// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K2 (curl_noise_pixel.h), K3 (noise_volume_pixel.h), K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
 // the CPU, so that the CPU test-suite (tests/test_host_build.py) can compare the product's kernel arithmetic with the oracle without a GPU.  The loops below do
 // what the kernels of reproject.cu / post_chain.cu do with the same functions; nothing here is linked into the product library.
 #define MM_HOST_BUILD 1
@@ -7,6 +7,7 @@
 
 #include "../../project-marshmallow_b200/csrc/curl_noise_pixel.h"
 #include "../../project-marshmallow_b200/csrc/curl_table.h"
+#include "../../project-marshmallow_b200/csrc/noise_volume_pixel.h"
 #include "../../project-marshmallow_b200/csrc/post_chain_pixel.h"
 #include "../../project-marshmallow_b200/csrc/reproject_pixel.h"
 
@@ -109,6 +110,26 @@ int hb_curl_noise(uint8_t *dst_rgba8) {
         uchar4 q = curl_pixel::curl_quantise(curls.data(), bounds, pix);
         dst_rgba8[4 * pix] = q.x; dst_rgba8[4 * pix + 1] = q.y; dst_rgba8[4 * pix + 2] = q.z; dst_rgba8[4 * pix + 3] = q.w;
     }
+    return 0;
+}
+
+// lowres_kernel / hires_kernel (noise_volumes.cu): the 32^3 volume whole, and the slices z = z0, z0 + zstep, ... of the 128^3 volume (the others stay untouched)
+int hb_noise_volumes(uint32_t seed, int z0, int zstep, uint8_t *low128_rgba8, uint8_t *hi32_rgba8) {
+    if (zstep <= 0) return -1;
+    for (int z = 0; z < 32; z++)
+        for (int y = 0; y < 32; y++)
+            for (int x = 0; x < 32; x++) {
+                uchar4 q = volume_pixel::hires_voxel(seed, x, y, z);
+                uint8_t *o = hi32_rgba8 + 4 * (((size_t)z * 32 + y) * 32 + x);
+                o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+            }
+    for (int z = z0; z < 128; z += zstep)
+        for (int y = 0; y < 128; y++)
+            for (int x = 0; x < 128; x++) {
+                uchar4 q = volume_pixel::lowres_voxel(seed, x, y, z);
+                uint8_t *o = low128_rgba8 + 4 * (((size_t)z * 128 + y) * 128 + x);
+                o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
+            }
     return 0;
 }
 

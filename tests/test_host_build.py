@@ -20,7 +20,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "project-marshmallow_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def hb():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("post_chain_pixel.h", "reproject_pixel.h", "curl_noise_pixel.h", "curl_table.h", "common.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("post_chain_pixel.h", "reproject_pixel.h", "curl_noise_pixel.h", "curl_table.h", "noise_volume_pixel.h", "common.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
                         "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-diag-suppress", "177", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--cudart", "static",
@@ -33,6 +33,7 @@ def hb():
     lib.hb_post_chain.argtypes = [p, i, i, f, f, f, p, i, p]
     lib.hb_reproject.argtypes = [p, p, p, i, i, p]
     lib.hb_curl_noise.argtypes = [p]
+    lib.hb_noise_volumes.argtypes = [C.c_uint32, i, i, p, p]
     return lib
 
 
@@ -98,3 +99,14 @@ def test_curl_noise_source_reproduces_the_shipped_texture(hb, assets, oracle):
     assert hb.hb_curl_noise(_ptr(got)) == 0
     assert np.array_equal(got, assets["curl"])
     assert np.array_equal(got, oracle.generate_curl_noise())
+
+
+@pytest.mark.parametrize("seed", [0, 12345])
+def test_noise_volume_source_equals_the_cpu_statement(hb, oracle, seed):
+    """K3 (our own generator; parity unpinned, no reference arithmetic exists): the kernel source on the CPU equals oracle/noise_volume_oracle.c byte for byte --
+    the 32^3 volume whole, every 21st slice of the 128^3 one."""
+    low, hi = oracle.build_noise_volumes(seed)
+    got_low, got_hi = np.zeros_like(low), np.zeros_like(hi)
+    assert hb.hb_noise_volumes(seed, 3, 21, _ptr(got_low), _ptr(got_hi)) == 0
+    assert np.array_equal(got_hi, hi)
+    assert np.array_equal(got_low[3::21], low[3::21])
