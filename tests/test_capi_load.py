@@ -31,6 +31,20 @@ def test_product_does_not_link_or_import_the_oracle(mm):
                 assert "liboracle" not in text and "oracle_binding" not in text, f"{f} references the oracle"
 
 
+def test_product_has_no_host_build_of_the_kernels(mm):
+    """The kernel source is written so that tests/host_build can compile it for the host (MM_HOST_BUILD) and hold it to the oracle; the product must never
+    do that: no build script or binding defines the macro, and the library carries neither the test harnesses' entry points nor host copies of the per-ray functions."""
+    import _pkg
+    for root, _, files in os.walk(_pkg.PKG_DIR):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp")) or f in ("Makefile",):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "define MM_HOST_BUILD" not in text and "-DMM_HOST_BUILD" not in text, f"{f} turns the host build on"
+    out = subprocess.run(["nm", "-C", mm.library_path()], capture_output=True, text=True).stdout
+    assert not [l for l in out.splitlines() if " hb_" in l or " hm_" in l]
+    assert "cloudTest" not in out and "reproject_texel" not in out and "god_ray_alpha" not in out, "host copies of device functions in the product library"
+
+
 def test_header_is_plain_c(tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     src = tmp_path / "t.c"
