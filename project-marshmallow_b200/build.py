@@ -14,7 +14,7 @@ LIB = os.environ.get("MM_LIB_OUT") or os.path.join(HERE, "libmarshmallow_b200.so
 DEMO = os.path.join(HERE, "frame_demo")
 CU_SOURCES = ["csrc/capi.cu", "csrc/cloud_march.cu", "csrc/cloud_march_fma.cu", "csrc/curl_noise.cu", "csrc/noise_volumes.cu", "csrc/tonemap.cu", "csrc/reproject.cu", "csrc/post_chain.cu"]
 CPP_SOURCES = ["host/sky_camera.cpp"]
-HEADERS = ["csrc/common.h", "csrc/cloud_march_x2.inl", "csrc/cloud_march_ray.inl", "csrc/cloud_march.cu", "csrc/post_chain_pixel.h", "csrc/reproject_pixel.h", "csrc/curl_noise_pixel.h", "csrc/curl_table.h", "csrc/noise_volume_pixel.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h", "host/ComputeShader.h", "host/frame_demo.cpp"]
+HEADERS = ["csrc/common.h", "csrc/cloud_march_x2.inl", "csrc/cloud_march_ray.inl", "csrc/cloud_march.cu", "csrc/post_chain_pixel.h", "csrc/reproject_pixel.h", "csrc/curl_noise_pixel.h", "csrc/curl_table.h", "csrc/noise_volume_pixel.h", "csrc/tonemap_pixel.h", "../include/marshmallow.h", "host/SkyManager.h", "host/Camera.h", "host/uniform_blocks.h", "host/ComputeShader.h", "host/frame_demo.cpp"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -1,4 +1,4 @@
-// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K2 (curl_noise_pixel.h), K3 (noise_volume_pixel.h), K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
+// aux_host.cu -- TEST INFRASTRUCTURE: the per-pixel source of K2 (curl_noise_pixel.h), K3 (noise_volume_pixel.h), K4 (tonemap_pixel.h), K5 (reproject_pixel.h) and K6 (post_chain_pixel.h) compiled for the HOST and run pixel by pixel on
 // the CPU, so that the CPU test-suite (tests/test_host_build.py) can compare the product's kernel arithmetic with the oracle without a GPU.  The loops below do
 // what the kernels of reproject.cu / post_chain.cu do with the same functions; nothing here is linked into the product library.
 #define MM_HOST_BUILD 1
@@ -10,6 +10,7 @@
 #include "../../project-marshmallow_b200/csrc/noise_volume_pixel.h"
 #include "../../project-marshmallow_b200/csrc/post_chain_pixel.h"
 #include "../../project-marshmallow_b200/csrc/reproject_pixel.h"
+#include "../../project-marshmallow_b200/csrc/tonemap_pixel.h"
 
 using namespace mm;
 
@@ -130,6 +131,15 @@ int hb_noise_volumes(uint32_t seed, int z0, int zstep, uint8_t *low128_rgba8, ui
                 uint8_t *o = low128_rgba8 + 4 * (((size_t)z * 128 + y) * 128 + x);
                 o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w;
             }
+    return 0;
+}
+
+// tonemap_kernel: the map the parity gate is defined on (RGBA32F -> RGBA8)
+int hb_tonemap(const float *src, size_t npix, uint8_t *dst_rgba8) {
+    for (size_t i = 0; i < npix; i++) {
+        uchar4 q = tonemap_pixel::tonemap_texel(make_float4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]));
+        dst_rgba8[4 * i] = q.x; dst_rgba8[4 * i + 1] = q.y; dst_rgba8[4 * i + 2] = q.z; dst_rgba8[4 * i + 3] = q.w;
+    }
     return 0;
 }
 

@@ -20,7 +20,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "project-marshmallow_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def hb():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("post_chain_pixel.h", "reproject_pixel.h", "curl_noise_pixel.h", "curl_table.h", "noise_volume_pixel.h", "common.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("post_chain_pixel.h", "reproject_pixel.h", "curl_noise_pixel.h", "curl_table.h", "noise_volume_pixel.h", "tonemap_pixel.h", "common.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-fmad=false",
                         "-prec-div=true", "-prec-sqrt=true", "-ftz=false", "-diag-suppress", "177", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "--cudart", "static",
@@ -34,6 +34,7 @@ def hb():
     lib.hb_reproject.argtypes = [p, p, p, i, i, p]
     lib.hb_curl_noise.argtypes = [p]
     lib.hb_noise_volumes.argtypes = [C.c_uint32, i, i, p, p]
+    lib.hb_tonemap.argtypes = [p, C.c_size_t, p]
     return lib
 
 
@@ -110,3 +111,15 @@ def test_noise_volume_source_equals_the_cpu_statement(hb, oracle, seed):
     assert hb.hb_noise_volumes(seed, 3, 21, _ptr(got_low), _ptr(got_hi)) == 0
     assert np.array_equal(got_hi, hi)
     assert np.array_equal(got_low[3::21], low[3::21])
+
+
+def test_tonemap_source_is_the_parity_gates_map(hb, oracle):
+    """K4 (tonemap.frag:11-28 without the vignette): the kernel source on the CPU against om_tonemap_rgba8 -- here both sides call the same C library's powf, so
+    the bytes are equal (on the GPU CUDA's powf may move a value by one step)."""
+    rng = np.random.default_rng(9)
+    src = np.concatenate([rng.random((4000, 4), dtype=np.float32) * 60.0, rng.random((4000, 4), dtype=np.float32) * 2.0 - 0.5,
+                          np.array([[0, 0, 0, 0], [50.2, 50.2, 50.2, 1], [1e9, -1.0, np.nan, 2.0]], np.float32)]).astype(np.float32)
+    got = np.zeros((len(src), 4), np.uint8)
+    assert hb.hb_tonemap(_ptr(src), len(src), _ptr(got)) == 0
+    want = oracle.tonemap_rgba8(src.reshape(1, -1, 4)).reshape(-1, 4)
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 1 and (got == want).mean() > 0.999
